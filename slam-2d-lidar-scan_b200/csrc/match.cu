@@ -1,0 +1,895 @@
+// Fused multi-resolution correlative scan matcher for a batch of particles (sm_100a).
+//
+// One persistent CTA per SM walks over particles; for each particle it runs the coarse and the fine stage of
+// ScanMatcher.matchScan (Utils/ScanMatcher_OGBased.py:47-79) entirely on chip, except for the fine likelihood
+// field which lives in a per-CTA global scratch slot (L2-resident):
+//
+//   window   visited/total window -> occupancy bits, scattered through the float64 index maps       (:20-37)
+//   blur     separable symmetric correlation in scipy's exact operation order, exploiting that the
+//            input takes two values {log(missProb), 0}; background tiles are skipped (their value is a
+//            host-computed constant produced by the same operation order)                            (:41-42)
+//   clamp    probMin = global min; prob[prob > 0.5*probMin] = 0                                       (:43-44)
+//   points   beam end points, compaction of beams < maxRange                                          (:81-89)
+//   lists    per theta: rotate, truncate to indices, sort + unique (lexicographic (x, y))             (:116-121)
+//   scores   per (theta, dy, dx): gather + numpy-pairwise sum + priors                                (:125-132)
+//   select   first-max argmax, or exp / pairwise sum / CDF inversion of one host uniform; confidence  (:133-141)
+//
+// Numerics: IEEE float64, no FMA contraction, numpy's pairwise-summation order and scipy's pair-add/multiply/
+// accumulate order are reproduced literally so that the score volume is bit-identical to the oracle's.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace slam {
+
+constexpr int NT = 512;       // threads per CTA
+constexpr int NW = NT / 32;   // warps per CTA
+constexpr unsigned FULL = 0xffffffffu;
+
+struct StageDev {
+  double unitLength, logMiss;
+  int r;                     // blur radius
+  double w[2 * SLAM_MAX_BLUR_RADIUS + 1];
+  double T1[SLAM_MAX_BLUR_RADIUS], T2[SLAM_MAX_BLUR_RADIUS];  // (c)*w[jj], (c+c)*w[jj]
+  double C0;                 // c*w[r]
+  double B1, B2;             // all-background value after the first / second pass
+  int nHalf, nOff, nTheta, nPoses;
+  const double *thetas, *cosT, *sinT;
+  int nLeaves;               // pairwise-sum leaves of the flattened score volume
+  const int2* leaves;        // (offset, length)
+  int progLen;               // postfix combine program: >= 0 push leaf, -1 add
+  const short* prog;
+  // ---- plan
+  int Wmax, Wmap, words, Ppitch, VbPitch, R, TB, Kpad, E;
+  int bitsInSmem, PInSmem, scoresInSmem, needScores;
+  int oBits, oVb, oNb, oAct, oRow, oCol, oP, oLists, oCnt, oScores, oDx, oDy, oLeaf;
+  size_t gBits, gP, gScores;  // byte offsets inside a CTA's global scratch slot
+};
+
+struct MatchParams {
+  int G, pitch, K, N;
+  double unit, mapX0, mapX1, mapY0, mapY1, fovHalf, maxRange, R;
+  const double *gridX, *gridY;
+  StageDev st[2];
+  const float* grid;
+  const double *ranges, *estPose, *rv, *tw, *uniforms;
+  double *outPose, *outConf;
+  int *outIdx, *status;
+  unsigned char* scratch;
+  size_t slotBytes;
+  double* dbgProb[2];
+  int* dbgDims[2];
+  double* dbgVol[2];
+  long long* dbgCycles;  // [gridDim][16] or null
+  int forceExactCdf;
+};
+
+// ------------------------------------------------------------------------------------------------ device
+__device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -1 - i : (i >= n ? 2 * n - 1 - i : i); }
+
+struct Fetch {
+  const unsigned* list;  // sorted unique keys (x << 16 | y)
+  const double* base;    // field pointer pre-offset by (dy, dx)
+  int pitch;
+  __device__ __forceinline__ double operator()(int k) const {
+    unsigned key = list[k];
+    return base[(int)(key & 0xffffu) * pitch + (int)(key >> 16)];
+  }
+};
+
+// numpy pairwise_sum, n <= 128 branch (8 running lanes, fixed tree, sequential tail)
+template <class F>
+__device__ __noinline__ double block_sum(const F f, int off, int n) {
+  if (n < 8) {
+    double res = 0.0;
+    for (int i = 0; i < n; ++i) res = dadd(res, f(off + i));
+    return res;
+  }
+  double r0 = f(off), r1 = f(off + 1), r2 = f(off + 2), r3 = f(off + 3);
+  double r4 = f(off + 4), r5 = f(off + 5), r6 = f(off + 6), r7 = f(off + 7);
+  int m = n - (n & 7);
+  for (int i = 8; i < m; i += 8) {
+    double a0 = f(off + i), a1 = f(off + i + 1), a2 = f(off + i + 2), a3 = f(off + i + 3);
+    double a4 = f(off + i + 4), a5 = f(off + i + 5), a6 = f(off + i + 6), a7 = f(off + i + 7);
+    r0 = dadd(r0, a0); r1 = dadd(r1, a1); r2 = dadd(r2, a2); r3 = dadd(r3, a3);
+    r4 = dadd(r4, a4); r5 = dadd(r5, a5); r6 = dadd(r6, a6); r7 = dadd(r7, a7);
+  }
+  double res = dadd(dadd(dadd(r0, r1), dadd(r2, r3)), dadd(dadd(r4, r5), dadd(r6, r7)));
+  for (int i = m; i < n; ++i) res = dadd(res, f(off + i));
+  return res;
+}
+
+// numpy pairwise_sum recursion (n > 128: split at n/2 rounded down to a multiple of 8); depth 3 covers n <= 512
+template <int D, class F>
+__device__ __forceinline__ double pairwise(const F& f, int off, int n) {
+  if (D == 0 || n <= 128) return block_sum(f, off, n);
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  double a = pairwise<(D > 0 ? D - 1 : 0)>(f, off, n2);
+  double b = pairwise<(D > 0 ? D - 1 : 0)>(f, off + n2, n - n2);
+  return dadd(a, b);
+}
+
+struct SmemVal {
+  const double* a;
+  __device__ __forceinline__ double operator()(int k) const { return a[k]; }
+};
+
+// bitonic sort of 32*E keys held E per lane (element index = lane*E + e), ascending
+template <int E>
+__device__ __forceinline__ void warp_sort(unsigned (&key)[E], int lane) {
+  constexpr int N = 32 * E;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j < E) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if ((e & j) == 0) {
+            const int e2 = e | j;
+            const int i = lane * E + e;
+            const bool up = (i & k) == 0;
+            unsigned a = key[e], b = key[e2];
+            unsigned lo = min(a, b), hi = max(a, b);
+            key[e] = up ? lo : hi;
+            key[e2] = up ? hi : lo;
+          }
+        }
+      } else {
+        const int lj = j / E;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          unsigned other = __shfl_xor_sync(FULL, key[e], lj);
+          const int i = lane * E + e;
+          const bool up = (i & k) == 0;
+          const bool lower = (lane & lj) == 0;
+          key[e] = (lower == up) ? min(key[e], other) : max(key[e], other);
+        }
+      }
+    }
+  }
+}
+
+// One theta: rotate the K0 end points, truncate to field indices, sort, unique -> list, count.
+template <int E>
+__device__ __forceinline__ void build_list(const double* dxs, const double* dys, int K0, double ox, double oy,
+                                           double c, double s, double bx, double by, double ul, int nHalf, int Wx,
+                                           int Wy, unsigned* list, int* cnt, int lane, int& status) {
+  unsigned key[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    int k = lane * E + e;
+    unsigned kk = 0xffffffffu;
+    if (k < K0) {
+      double ddx = dxs[k], ddy = dys[k];
+      // ScanMatcher.rotate :169-170 -- evaluated left to right
+      double qx = dsub(dadd(ox, dmul(c, ddx)), dmul(s, ddy));
+      double qy = dadd(dadd(oy, dmul(s, ddx)), dmul(c, ddy));
+      int xi = (int)ddiv(dsub(qx, bx), ul);   // :174-175 astype(int) truncates toward zero
+      int yi = (int)ddiv(dsub(qy, by), ul);
+      if (xi - nHalf < 0 || xi + nHalf >= Wx || yi - nHalf < 0 || yi + nHalf >= Wy) {
+        status |= SLAM_ST_INDEX_OUT_OF_FIELD;
+        xi = min(max(xi, nHalf), Wx - 1 - nHalf);
+        yi = min(max(yi, nHalf), Wy - 1 - nHalf);
+      }
+      kk = ((unsigned)xi << 16) | (unsigned)yi;
+    }
+    key[e] = kk;
+  }
+  warp_sort<E>(key, lane);
+  // unique: keep element i if it differs from element i-1
+  unsigned prevLast = __shfl_up_sync(FULL, key[E - 1], 1);
+  int mine = 0;
+  bool keep[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    unsigned prev = (e == 0) ? prevLast : key[e - 1];
+    bool first = (e == 0 && lane == 0);
+    keep[e] = key[e] != 0xffffffffu && (first || key[e] != prev);
+    mine += keep[e] ? 1 : 0;
+  }
+  int incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int v = __shfl_up_sync(FULL, incl, d);
+    if (lane >= d) incl += v;
+  }
+  int pos = incl - mine;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    if (keep[e]) list[pos++] = key[e];
+  }
+  int total = __shfl_sync(FULL, incl, 31);
+  if (lane == 0) *cnt = total;
+}
+
+struct BlockScratch {
+  double dval[NW];
+  int ival[NW];
+  double bcast[4];
+  int ibcast[8];
+};
+
+__device__ __forceinline__ double block_min(double v, BlockScratch& bs) {
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, d));
+  __syncthreads();
+  if (lane == 0) bs.dval[warp] = v;
+  __syncthreads();
+  double r = bs.dval[0];
+  for (int i = 1; i < NW; ++i) r = fmin(r, bs.dval[i]);
+  return r;
+}
+
+struct StageOut {
+  double x, y, th, conf;
+  int it, ia, ib;
+};
+
+__device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, int p, double cx, double cy, double cth,
+                          bool sample, double uniform, unsigned char* smem, unsigned char* gslot, BlockScratch& bs,
+                          int& status, StageOut& out, long long* cyc) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double ul = S.unitLength;
+  const int r = S.r;
+
+  // ---- A. geometry of the search window (ScanMatcher_OGBased.py:21-28)
+  const double xr0 = dsub(cx, P.R), xr1 = dadd(cx, P.R);
+  const double yr0 = dsub(cy, P.R), yr1 = dadd(cy, P.R);
+  const int Wx = (int)ddiv(dsub(xr1, xr0), ul) + 1;
+  const int Wy = (int)ddiv(dsub(yr1, yr0), ul) + 1;
+  int mx0 = (int)rint(ddiv(dsub(xr0, P.mapX0), P.unit)), mx1 = (int)rint(ddiv(dsub(xr1, P.mapX0), P.unit));
+  int my0 = (int)rint(ddiv(dsub(yr0, P.mapY0), P.unit)), my1 = (int)rint(ddiv(dsub(yr1, P.mapY0), P.unit));
+  if (xr0 < P.mapX0 || xr1 > P.mapX1 || yr0 < P.mapY0 || yr1 > P.mapY1) status |= SLAM_ST_WINDOW_OUTSIDE_MAP;
+  mx0 = max(mx0, 0); my0 = max(my0, 0);
+  mx1 = min(mx1, P.G); my1 = min(my1, P.G);
+  mx1 = min(mx1, mx0 + S.Wmap); my1 = min(my1, my0 + S.Wmap);
+  const int ncols = max(mx1 - mx0, 0), nrows = max(my1 - my0, 0);
+  const int words = S.words;
+  const int nStrips = (Wx + 31) >> 5;
+
+  unsigned* bits = S.bitsInSmem ? (unsigned*)(smem + S.oBits) : (unsigned*)(gslot + S.gBits);
+  double* Vb = (double*)(smem + S.oVb);
+  unsigned* nb = (unsigned*)(smem + S.oNb);          // [R][words + 2]
+  unsigned* act = (unsigned*)(smem + S.oAct);        // [Wmax][actWords]
+  short* rowMap = (short*)(smem + S.oRow);
+  short* colMap = (short*)(smem + S.oCol);
+  double* Pf = S.PInSmem ? (double*)(smem + S.oP) : (double*)(gslot + S.gP);
+  const int Pp = S.Ppitch;
+  const int actWords = (words + 31) >> 5;
+
+  __syncthreads();  // previous users of the arena are done
+  if (cyc && tid == 0) cyc[0] -= clock64();
+
+  // ---- B. clear bitmap, float64 index maps (:36 via :173-176) -- rows of OccupancyGridX are identical
+  for (int i = tid; i < Wy * words; i += NT) bits[i] = 0u;
+  for (int i = tid; i < Wy * actWords; i += NT) act[i] = 0u;
+  for (int i = tid; i < S.R * (words + 2); i += NT) nb[i] = 0u;
+  for (int j = tid; j < ncols; j += NT) {
+    int c = (int)ddiv(dsub(P.gridX[mx0 + j], xr0), ul);
+    if (c < 0 || c >= Wx) { status |= SLAM_ST_INDEX_OUT_OF_FIELD; c = min(max(c, 0), Wx - 1); }
+    colMap[j] = (short)c;
+  }
+  for (int i = tid; i < nrows; i += NT) {
+    int c = (int)ddiv(dsub(P.gridY[my0 + i], yr0), ul);
+    if (c < 0 || c >= Wy) { status |= SLAM_ST_INDEX_OUT_OF_FIELD; c = min(max(c, 0), Wy - 1); }
+    rowMap[i] = (short)c;
+  }
+  __syncthreads();
+
+  // ---- C. stream the window: occupied <=> visited/total > 0.5 <=> 2*visited > total (:29-31), scatter (:37)
+  {
+    const float* g = P.grid + (size_t)p * P.G * P.pitch * 2;
+    const int mxa = mx0 & ~1;                         // 16-byte aligned start
+    const int npairs = (mx1 - mxa + 1) >> 1;
+    for (int i = warp; i < nrows; i += NW) {
+      const float4* rowp = (const float4*)(g + ((size_t)(my0 + i) * P.pitch + mxa) * 2);
+      const int rbase = (int)rowMap[i] * words;
+      for (int q0 = 0; q0 < npairs; q0 += 8 * 32) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          int q = q0 + u * 32 + lane;
+          v[u] = (q < npairs) ? ld_stream_f4(rowp + q) : make_float4(0.f, 1.f, 0.f, 1.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          int q = q0 + u * 32 + lane;
+          int j0 = mxa + 2 * q - mx0;                // window column of the first cell of the pair
+          if (2.f * v[u].x > v[u].y && j0 >= 0 && j0 < ncols) {
+            int c = colMap[j0];
+            atomicOr(&bits[rbase + (c >> 5)], 1u << (c & 31));
+          }
+          if (2.f * v[u].z > v[u].w && j0 + 1 >= 0 && j0 + 1 < ncols) {
+            int c = colMap[j0 + 1];
+            atomicOr(&bits[rbase + (c >> 5)], 1u << (c & 31));
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (cyc && tid == 0) { long long t = clock64(); cyc[0] += t; cyc[1] -= t; }
+
+  // ---- D. separable blur in scipy's order, chunk of R rows at a time
+  double mn = 0.0;   // every field value is <= 0
+  for (int i0 = 0; i0 < Wy; i0 += S.R) {
+    const int rows = min(S.R, Wy - i0);
+    // first pass (axis 0): depends only on the 2r+1 occupancy bits of the column
+    for (int s = warp; s < nStrips; s += NW) {
+      unsigned sr = 0;
+      for (int d = -r; d <= r; ++d) {
+        unsigned wv = bits[reflect_idx(i0 + d, Wy) * words + s];
+        sr |= ((wv >> lane) & 1u) << (d + r);
+      }
+      const int j = 32 * s + lane;
+      for (int ii = 0; ii < rows; ++ii) {
+        if (ii > 0) {
+          unsigned wv = bits[reflect_idx(i0 + ii + r, Wy) * words + s];
+          sr = (sr >> 1) | (((wv >> lane) & 1u) << (2 * r));
+        }
+        unsigned nbm = __ballot_sync(FULL, sr != 0u);
+        double v = S.B1;
+        if (nbm != 0u) {
+          v = ((sr >> r) & 1u) ? 0.0 : S.C0;
+          for (int jj = 0; jj < r; ++jj) {
+            int occ = (int)((sr >> jj) & 1u) + (int)((sr >> (2 * r - jj)) & 1u);
+            double t = occ == 0 ? S.T2[jj] : (occ == 1 ? S.T1[jj] : 0.0);
+            v = dadd(v, t);
+          }
+        }
+        if (j < Wx) Vb[ii * S.VbPitch + r + j] = v;
+        if (lane == 0) nb[ii * (words + 2) + s + 1] = nbm;
+      }
+    }
+    __syncthreads();
+    // reflect halo of the row buffer
+    for (int t = tid; t < rows * 2 * r; t += NT) {
+      int ii = t / (2 * r), k = t % (2 * r);
+      double* row = Vb + ii * S.VbPitch + r;
+      if (k < r) row[-1 - k] = row[k];
+      else { int kk = k - r; row[Wx + kk] = row[Wx - 1 - kk]; }
+    }
+    __syncthreads();
+    // second pass (axis 1)
+    for (int t = warp; t < rows * nStrips; t += NW) {
+      const int ii = t / nStrips, s = t - ii * nStrips;
+      const unsigned* nbr = nb + ii * (words + 2) + s;
+      const unsigned lo = nbr[0], m = nbr[1], hi = (s + 1 < nStrips) ? nbr[2] : 0u;
+      unsigned dil = m;
+      for (int k = 1; k <= r; ++k) dil |= (m << k) | (m >> k) | (lo >> (32 - k)) | (hi << (32 - k));
+      const int j = 32 * s + lane;
+      double val = S.B2;
+      if (dil != 0u) {
+        if ((dil >> lane) & 1u) {
+          const double* c = Vb + ii * S.VbPitch + r + j;
+          val = dmul(c[0], S.w[r]);
+          for (int jj = 0; jj < r; ++jj) val = dadd(val, dmul(dadd(c[jj - r], c[r - jj]), S.w[jj]));
+        }
+        if (lane == 0) atomicOr(&act[(i0 + ii) * actWords + (s >> 5)], 1u << (s & 31));
+      }
+      if (j < Wx) {
+        Pf[(size_t)(i0 + ii) * Pp + j] = val;
+        mn = fmin(mn, val);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- E. probMin, clamp (:43-44); only tiles that are not pure background can exceed the threshold
+  const double probMin = block_min(mn, bs);
+  const double thr = dmul(0.5, probMin);
+  for (int t = warp; t < Wy * nStrips; t += NW) {
+    const int i = t / nStrips, s = t - i * nStrips;
+    if ((act[i * actWords + (s >> 5)] >> (s & 31)) & 1u) {
+      const int j = 32 * s + lane;
+      if (j < Wx) {
+        double* q = Pf + (size_t)i * Pp + j;
+        if (*q > thr) *q = 0.0;
+      }
+    }
+  }
+  __syncthreads();
+  if (cyc && tid == 0) { long long t = clock64(); cyc[1] += t; cyc[2] -= t; }
+  if (P.dbgProb[stageId]) {
+    double* d = P.dbgProb[stageId] + (size_t)p * S.Wmax * S.Wmax;
+    for (int i = tid; i < Wy * Wx; i += NT) d[(i / Wx) * S.Wmax + (i % Wx)] = Pf[(size_t)(i / Wx) * Pp + (i % Wx)];
+    if (tid == 0) { P.dbgDims[stageId][2 * p] = Wy; P.dbgDims[stageId][2 * p + 1] = Wx; }
+  }
+
+  // ---- F. beam end points (:81-89) with order-preserving compaction of beams < maxRange
+  double* dxs = (double*)(smem + S.oDx);
+  double* dys = (double*)(smem + S.oDy);
+  int K0;
+  {
+    const int K = P.K;
+    const double start = dsub(cth, P.fovHalf), stop = dadd(cth, P.fovHalf);
+    const double step = ddiv(dsub(stop, start), (double)(K - 1));
+    int base = 0;
+    for (int k0 = 0; k0 < K; k0 += NT) {     // K <= 512 -> one trip
+      const int k = k0 + tid;
+      bool keep = false;
+      double ddx = 0, ddy = 0;
+      if (k < K) {
+        const double rm = P.ranges[k];
+        keep = rm < P.maxRange;
+        const double ang = (k == K - 1) ? stop : dadd(dmul((double)k, step), start);   // np.linspace
+        double sn, cs;
+        sincos(ang, &sn, &cs);
+        const double px = dadd(cx, dmul(cs, rm)), py = dadd(cy, dmul(sn, rm));
+        ddx = dsub(px, cx); ddy = dsub(py, cy);                                          // (px - ox) of :169
+      }
+      unsigned bal = __ballot_sync(FULL, keep);
+      __syncthreads();
+      if (lane == 0) bs.ival[warp] = __popc(bal);
+      __syncthreads();
+      int before = base;
+      for (int w2 = 0; w2 < warp; ++w2) before += bs.ival[w2];
+      int tot = 0;
+      for (int w2 = 0; w2 < NW; ++w2) tot += bs.ival[w2];
+      if (keep) {
+        int pos = before + __popc(bal & ((1u << lane) - 1u));
+        dxs[pos] = ddx; dys[pos] = ddy;
+      }
+      base += tot;
+    }
+    K0 = base;
+  }
+  __syncthreads();
+
+  // ---- G. per-theta lists + score volume, TB thetas at a time
+  unsigned* lists = (unsigned*)(smem + S.oLists);
+  int* cnts = (int*)(smem + S.oCnt);
+  double* scores = S.needScores ? (S.scoresInSmem ? (double*)(smem + S.oScores) : (double*)(gslot + S.gScores)) : nullptr;
+  double* dvol = P.dbgVol[stageId] ? P.dbgVol[stageId] + (size_t)p * S.nPoses : nullptr;
+  const int nOff = S.nOff, nOff2 = nOff * nOff;
+  const double* rv = (stageId == 0) ? P.rv : nullptr;
+  const double* tw = (stageId == 0 && P.tw) ? P.tw + (size_t)p * nOff2 : nullptr;
+  double best = 0.0;
+  int bestIdx = -1;
+  bool sawNan = false;
+  for (int t0 = 0; t0 < S.nTheta; t0 += S.TB) {
+    const int nt = min(S.TB, S.nTheta - t0);
+    if (cyc && tid == 0) cyc[3] -= clock64();
+    for (int tl = warp; tl < nt; tl += NW) {
+      const double c = S.cosT[t0 + tl], s = S.sinT[t0 + tl];
+      if (S.E == 8)
+        build_list<8>(dxs, dys, K0, cx, cy, c, s, xr0, yr0, ul, S.nHalf, Wx, Wy, lists + tl * S.Kpad, cnts + tl, lane, status);
+      else
+        build_list<16>(dxs, dys, K0, cx, cy, c, s, xr0, yr0, ul, S.nHalf, Wx, Wy, lists + tl * S.Kpad, cnts + tl, lane, status);
+    }
+    __syncthreads();
+    if (cyc && tid == 0) { long long t = clock64(); cyc[3] += t; cyc[4] -= t; }
+    const int nq = nt * nOff2;
+    for (int q = tid; q < nq; q += NT) {
+      const int tl = q / nOff2, rem = q - tl * nOff2;
+      const int a = rem / nOff, b = rem - a * nOff;
+      Fetch f;
+      f.list = lists + tl * S.Kpad;
+      f.base = Pf + (a - S.nHalf) * Pp + (b - S.nHalf);
+      f.pitch = Pp;
+      double sc = pairwise<3>(f, 0, cnts[tl]);                     // np.sum(axis=2) :130
+      if (rv) sc = dadd(sc, rv[rem]);                              // + rv + thetaWeight :131
+      if (tw) sc = dadd(sc, tw[rem]);
+      const int flat = (t0 + tl) * nOff2 + rem;
+      if (scores) scores[flat] = sc;
+      if (dvol) dvol[flat] = sc;
+      if (sc != sc) sawNan = true;
+      if (bestIdx < 0 || sc > best) { best = sc; bestIdx = flat; }  // flat increases per thread -> first max kept
+    }
+    __syncthreads();
+    if (cyc && tid == 0) cyc[4] += clock64();
+  }
+  if (cyc && tid == 0) cyc[5] -= clock64();
+
+  // ---- H. select (:133-141)
+  if (__syncthreads_or(sawNan ? 1 : 0)) status |= SLAM_ST_NAN_SCORE;
+  int chosen;
+  {  // first maximum in C order
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      double ob = __shfl_xor_sync(FULL, best, d);
+      int oi = __shfl_xor_sync(FULL, bestIdx, d);
+      if (oi >= 0 && (bestIdx < 0 || ob > best || (ob == best && oi < bestIdx))) { best = ob; bestIdx = oi; }
+    }
+    if (lane == 0) { bs.dval[warp] = best; bs.ival[warp] = bestIdx; }
+    __syncthreads();
+    double b = bs.dval[0];
+    int bi = bs.ival[0];
+    for (int w2 = 1; w2 < NW; ++w2) {
+      double ob = bs.dval[w2];
+      int oi = bs.ival[w2];
+      if (oi >= 0 && (bi < 0 || ob > b || (ob == b && oi < bi))) { b = ob; bi = oi; }
+    }
+    chosen = bi;
+    __syncthreads();
+  }
+  double conf = 0.0;
+  if (S.needScores) {
+    const int n = S.nPoses;
+    for (int i = tid; i < n; i += NT) scores[i] = exp(scores[i]);
+    __syncthreads();
+    double* leafSum = (double*)(smem + S.oLeaf);
+    SmemVal sv;
+    sv.a = scores;
+    for (int l = tid; l < S.nLeaves; l += NT) {
+      int2 lf = S.leaves[l];
+      leafSum[l] = block_sum(sv, lf.x, lf.y);
+    }
+    __syncthreads();
+    if (tid == 0) {   // combine the leaves along numpy's recursion tree
+      double stack[24];
+      int sp = 0;
+      for (int i = 0; i < S.progLen; ++i) {
+        int op = S.prog[i];
+        if (op >= 0) stack[sp++] = leafSum[op];
+        else { sp--; stack[sp - 1] = dadd(stack[sp - 1], stack[sp]); }
+      }
+      bs.bcast[0] = stack[0];
+    }
+    __syncthreads();
+    conf = bs.bcast[0];
+    if (sample) {
+      // np.random.choice: p = e / e.sum(); cdf = cumsum(p) (sequential); cdf /= cdf[-1]; searchsorted(u, 'right').
+      // Parallel prefix with a certified margin; the exact sequential walk only when u is within the rounding
+      // envelope of a CDF step (probability ~1e-10 per call).
+      const int chunk = (n + NT - 1) / NT;
+      const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
+      double part = 0.0;
+      for (int i = lo; i < hi; ++i) part += ddiv(scores[i], conf);
+      // block exclusive scan of the chunk sums
+      double incl = part;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        double v = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += v;
+      }
+      if (lane == 31) bs.dval[warp] = incl;
+      __syncthreads();
+      double wbase = 0.0, total = 0.0;
+      for (int w2 = 0; w2 < NW; ++w2) {
+        if (w2 < warp) wbase += bs.dval[w2];
+        total += bs.dval[w2];
+      }
+      const double before = wbase + incl - part;
+      if (tid == 0) { bs.ibcast[0] = -1; bs.ibcast[1] = 0; }
+      __syncthreads();
+      const double tol = 1e-10;
+      if (hi > lo && before / total <= uniform && ((before + part) / total > uniform || hi == n)) {
+        double c = before, prev = before;
+        int found = -1;
+        for (int i = lo; i < hi; ++i) {
+          prev = c;
+          c += ddiv(scores[i], conf);
+          if (c / total > uniform) { found = i; break; }
+        }
+        if (found >= 0) {
+          bool amb = (uniform - prev / total) < tol || (c / total - uniform) < tol;
+          // several threads can only claim when chunks tie within rounding -> treated as ambiguous below
+          int old = atomicExch(&bs.ibcast[0], found);
+          if (old != -1 || amb) bs.ibcast[1] = 1;
+        }
+      }
+      __syncthreads();
+      int idx = bs.ibcast[0];
+      bool exact = P.forceExactCdf || idx < 0 || bs.ibcast[1];
+      __syncthreads();
+      if (exact) {
+        if (tid == 0) {
+          double c = 0.0;
+          for (int i = 0; i < n; ++i) c = dadd(c, ddiv(scores[i], conf));
+          const double last = c;
+          c = 0.0;
+          int found = n;
+          for (int i = 0; i < n; ++i) {
+            c = dadd(c, ddiv(scores[i], conf));
+            if (ddiv(c, last) > uniform) { found = i; break; }
+          }
+          bs.ibcast[0] = min(found, n - 1);
+        }
+        __syncthreads();
+        idx = bs.ibcast[0];
+      }
+      chosen = idx;
+    }
+  }
+  if (chosen < 0) chosen = 0;
+  const int it = chosen / nOff2, rem = chosen - it * nOff2;
+  const int ia = rem / nOff, ib = rem - ia * nOff;
+  out.it = it; out.ia = ia; out.ib = ib;
+  out.x = dadd(cx, dmul((double)(ib - S.nHalf), ul));      // :142-143
+  out.y = dadd(cy, dmul((double)(ia - S.nHalf), ul));
+  out.th = dadd(cth, S.thetas[it]);
+  out.conf = conf;
+  if (cyc && tid == 0) cyc[5] += clock64();
+}
+
+__global__ void __launch_bounds__(NT, 1) match_kernel(const __grid_constant__ MatchParams P) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ BlockScratch bs;
+  unsigned char* gslot = P.scratch + (size_t)blockIdx.x * P.slotBytes;
+  long long* cyc = P.dbgCycles ? P.dbgCycles + (size_t)blockIdx.x * 16 : nullptr;
+  for (int p = blockIdx.x; p < P.N; p += gridDim.x) {
+    const double x = P.estPose[3 * p], y = P.estPose[3 * p + 1], th = P.estPose[3 * p + 2];
+    int status = 0;
+    StageOut c, f;
+    const bool sample = P.uniforms != nullptr;
+    run_stage(P, P.st[0], 0, p, x, y, th, sample, sample ? P.uniforms[p] : 0.0, smem, gslot, bs, status, c, cyc);
+    run_stage(P, P.st[1], 1, p, c.x, c.y, c.th, false, 0.0, smem, gslot, bs, status, f, cyc ? cyc + 8 : nullptr);
+    status = __syncthreads_or(status);
+    if (threadIdx.x == 0) {
+      P.outPose[3 * p] = f.x; P.outPose[3 * p + 1] = f.y; P.outPose[3 * p + 2] = f.th;
+      P.outConf[p] = c.conf;
+      int* o = P.outIdx + 6 * p;
+      o[0] = c.it; o[1] = c.ia; o[2] = c.ib; o[3] = f.it; o[4] = f.ia; o[5] = f.ib;
+      P.status[p] = status;
+    }
+  }
+}
+
+// heading prior (ScanMatcher_OGBased.py:105-108)
+__global__ void priors_kernel(int N, int nHalf, double coef, const double* phi, const int* hasPhi, double* tw) {
+  const int nOff = 2 * nHalf + 1, nOff2 = nOff * nOff;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * nOff2) return;
+  const int p = (int)(i / nOff2), rem = (int)(i - (long long)p * nOff2);
+  if (!hasPhi[p]) { tw[i] = 0.0; return; }
+  const int a = rem / nOff, b = rem - a * nOff;
+  const int xv = b - nHalf, yv = a - nHalf;
+  double dist = sqrt((double)(xv * xv + yv * yv));
+  if (dist == 0.0) dist = 0.0001;
+  const double ph = phi[p];
+  const double num = dadd(dmul((double)xv, cos(ph)), dmul((double)yv, sin(ph)));
+  const double ang = acos(ddiv(num, dist));
+  tw[i] = dmul(coef, dmul(ang, ang));
+}
+
+}  // namespace slam
+
+// ------------------------------------------------------------------------------------------------ host
+using namespace slam;
+
+struct slam_matcher {
+  MatchParams P;
+  std::vector<void*> owned;
+  size_t smemBytes;
+  int numCtas;
+  size_t workspaceBytes;
+};
+
+static void leaves_rec(int off, int n, std::vector<int2>& leaves, std::vector<short>& prog) {
+  if (n <= 128) {
+    prog.push_back((short)leaves.size());
+    leaves.push_back(make_int2(off, n));
+    return;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  leaves_rec(off, n2, leaves, prog);
+  leaves_rec(off + n2, n - n2, leaves, prog);
+  prog.push_back(-1);
+}
+
+template <class T>
+static int upload(slam_matcher* m, const T* h, size_t n, const T** d) {
+  void* p = nullptr;
+  SLAM_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  m->owned.push_back(p);
+  SLAM_CUDA(cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice));
+  *d = (const T*)p;
+  return 0;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int plan_stage(slam_matcher* m, const slam_geometry* g, const slam_stage_desc& d, double R, int stageId,
+                      StageDev& S, size_t& smemNeed, size_t& slotBytes, size_t smemBudget) {
+  if (d.blurRadius < 1 || d.blurRadius > SLAM_MAX_BLUR_RADIUS) return fail(SLAM_E_UNSUPPORTED, "blur radius must be 1..8");
+  if (g->K < 2 || g->K > SLAM_MAX_BEAMS) return fail(SLAM_E_UNSUPPORTED, "beams per scan must be 2..512");
+  S.unitLength = d.unitLength;
+  S.logMiss = d.logMiss;
+  S.r = d.blurRadius;
+  const int r = S.r;
+  const double c = d.logMiss;
+  for (int i = 0; i < 2 * r + 1; ++i) S.w[i] = d.blurW[i];
+  // all constants with the same (non-fused) operation order the kernel / scipy use
+  volatile double t;
+  t = c * S.w[r]; S.C0 = t;
+  for (int jj = 0; jj < r; ++jj) {
+    t = c * S.w[jj]; S.T1[jj] = t;
+    volatile double cc = c + c;
+    t = cc * S.w[jj]; S.T2[jj] = t;
+  }
+  volatile double b1 = S.C0;
+  for (int jj = 0; jj < r; ++jj) { volatile double u = b1 + S.T2[jj]; b1 = u; }
+  S.B1 = b1;
+  volatile double b2 = S.B1 * S.w[r];
+  for (int jj = 0; jj < r; ++jj) {
+    volatile double pr = S.B1 + S.B1;
+    volatile double pm = pr * S.w[jj];
+    volatile double u = b2 + pm;
+    b2 = u;
+  }
+  S.B2 = b2;
+  S.nHalf = d.nHalf;
+  S.nOff = 2 * d.nHalf + 1;
+  S.nTheta = d.nTheta;
+  S.nPoses = S.nTheta * S.nOff * S.nOff;
+  if (upload(m, d.h_thetas, d.nTheta, &S.thetas) || upload(m, d.h_cos, d.nTheta, &S.cosT) ||
+      upload(m, d.h_sin, d.nTheta, &S.sinT))
+    return 1;
+  std::vector<int2> leaves;
+  std::vector<short> prog;
+  leaves_rec(0, S.nPoses, leaves, prog);
+  if (leaves.size() > 30000) return fail(SLAM_E_UNSUPPORTED, "score volume too large");
+  S.nLeaves = (int)leaves.size();
+  S.progLen = (int)prog.size();
+  if (upload(m, leaves.data(), leaves.size(), &S.leaves) || upload(m, prog.data(), prog.size(), &S.prog)) return 1;
+
+  // ---- memory plan
+  S.Wmax = (int)(2.0 * R / d.unitLength) + 2;
+  S.Wmap = (int)(2.0 * R / g->unit) + 3;
+  if (S.Wmax > 32000 || S.Wmap > 32000) return fail(SLAM_E_UNSUPPORTED, "search window too large");
+  S.words = (S.Wmax + 31) / 32;
+  S.Kpad = (g->K + 3) & ~3;
+  S.E = g->K <= 256 ? 8 : 16;
+  S.needScores = (stageId == 0);
+  const int actWords = (S.words + 31) / 32;
+  const size_t bitsBytes = (size_t)S.Wmax * S.words * 4;
+  const size_t actBytes = (size_t)S.Wmax * actWords * 4;
+  const size_t mapBytes = align_up((size_t)S.Wmap * 2, 16);
+  const size_t scoreBytes = S.needScores ? (size_t)S.nPoses * 8 : 0;
+  const size_t leafBytes = S.needScores ? (size_t)S.nLeaves * 8 : 0;
+  const size_t dxyBytes = align_up((size_t)g->K * 8, 16);
+  // field pitch: conflict-free shared-memory gathers want pitch == nOff (mod 16) doubles
+  int pp = S.Wmax;
+  while ((pp % 16) != (S.nOff % 16)) ++pp;
+  S.Ppitch = pp;
+  const size_t PBytes = (size_t)S.Wmax * S.Ppitch * 8;
+  S.VbPitch = S.Wmax + 2 * r;
+  // try placements from fastest to most frugal
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    S.PInSmem = (attempt & 4) ? 0 : (stageId == 0);     // fine field always in the global slot
+    S.scoresInSmem = (attempt & 2) ? 0 : 1;
+    S.bitsInSmem = (attempt & 1) ? 0 : 1;
+    for (int Rr : {16, 8, 4, 2}) {
+      for (int TB : {S.nTheta, (S.nTheta + 1) / 2, NW, 8, 4}) {
+        if (TB > S.nTheta || TB < 1) continue;
+        S.R = Rr;
+        S.TB = TB;
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return (int)o; };
+        S.oP = S.PInSmem ? take(PBytes) : 0;
+        S.oAct = take(actBytes);
+        S.oDx = take(dxyBytes);
+        S.oDy = take(dxyBytes);
+        const size_t common = off;
+        // blur-phase buffers
+        S.oBits = S.bitsInSmem ? take(bitsBytes) : 0;
+        S.oVb = take((size_t)Rr * S.VbPitch * 8);
+        S.oNb = take((size_t)Rr * (S.words + 2) * 4);
+        S.oRow = take(mapBytes);
+        S.oCol = take(mapBytes);
+        const size_t blurEnd = off;
+        // correlate-phase buffers alias the blur-phase ones
+        off = common;
+        S.oLists = take((size_t)TB * S.Kpad * 4);
+        S.oCnt = take((size_t)TB * 4);
+        S.oScores = (S.needScores && S.scoresInSmem) ? take(scoreBytes) : 0;
+        S.oLeaf = take(leafBytes);
+        const size_t need = std::max(blurEnd, off);
+        if (need <= smemBudget) {
+          smemNeed = std::max(smemNeed, need);
+          size_t g0 = slotBytes;
+          S.gBits = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsBytes, 256);
+          S.gP = g0; g0 += S.PInSmem ? 0 : align_up(PBytes, 256);
+          S.gScores = g0; g0 += (S.needScores && !S.scoresInSmem) ? align_up(scoreBytes, 256) : 0;
+          slotBytes = g0;
+          return 0;
+        }
+      }
+    }
+  }
+  return fail(SLAM_E_UNSUPPORTED, "stage does not fit the shared-memory plan");
+}
+
+extern "C" int slam_matcher_create(const slam_geometry* g, const slam_matcher_desc* d, slam_matcher** out) {
+  if (!g || !d || !out) return fail(SLAM_E_BADARG, "null argument");
+  if (g->pitch % 4 || g->pitch < g->G) return fail(SLAM_E_BADARG, "pitch must be a multiple of 4 cells and >= G");
+  slam_matcher* m = new slam_matcher();
+  MatchParams& P = m->P;
+  memset(&P, 0, sizeof(P));
+  P.G = g->G; P.pitch = g->pitch; P.K = g->K;
+  P.unit = g->unit; P.mapX0 = g->mapX0; P.mapX1 = g->mapX1; P.mapY0 = g->mapY0; P.mapY1 = g->mapY1;
+  P.fovHalf = g->fovHalf; P.maxRange = g->maxRange; P.R = d->windowRadius;
+  P.gridX = g->d_gridX; P.gridY = g->d_gridY;
+  int dev = 0, smemMax = 0, sms = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || smemMax <= 0) {
+    smemMax = 227 * 1024;   // sm_100a; lets the planner run on a GPU-less build box
+    cudaGetLastError();
+  }
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+    sms = 148;
+    cudaGetLastError();
+  }
+  const size_t budget = (size_t)smemMax - 1024;   // static shared + reserve
+  size_t smemNeed = 0, slot = 0;
+  for (int s = 0; s < 2; ++s) {
+    int rc = plan_stage(m, g, s == 0 ? d->coarse : d->fine, d->windowRadius, s, P.st[s], smemNeed, slot, budget);
+    if (rc) { slam_matcher_destroy(m); return rc; }
+  }
+  m->smemBytes = smemNeed;
+  P.slotBytes = align_up(slot, 256);
+  m->numCtas = sms;
+  m->workspaceBytes = P.slotBytes * (size_t)m->numCtas + 256;
+  *out = m;
+  return 0;
+}
+
+extern "C" void slam_matcher_destroy(slam_matcher* m) {
+  if (!m) return;
+  for (void* p : m->owned) cudaFree(p);
+  delete m;
+}
+
+extern "C" size_t slam_matcher_workspace_bytes(const slam_matcher* m) { return m ? m->workspaceBytes : 0; }
+extern "C" int slam_matcher_field_side(const slam_matcher* m, int stage) { return m->P.st[stage & 1].Wmax; }
+extern "C" int slam_matcher_num_poses(const slam_matcher* m, int stage) { return m->P.st[stage & 1].nPoses; }
+
+// test / profiling hooks (not part of the reference surface)
+extern "C" void slam_matcher_set_debug(slam_matcher* m, long long* d_cycles, int forceExactCdf) {
+  m->P.dbgCycles = d_cycles;
+  m->P.forceExactCdf = forceExactCdf;
+}
+extern "C" int slam_matcher_num_ctas(const slam_matcher* m) { return m->numCtas; }
+extern "C" int slam_matcher_plan(const slam_matcher* m, int stage, int* out8) {
+  const StageDev& S = m->P.st[stage & 1];
+  out8[0] = S.PInSmem; out8[1] = S.scoresInSmem; out8[2] = S.bitsInSmem; out8[3] = S.R;
+  out8[4] = S.TB; out8[5] = S.Ppitch; out8[6] = (int)m->smemBytes; out8[7] = (int)(m->P.slotBytes >> 10);
+  return 0;
+}
+
+extern "C" int slam_match_scan(slam_matcher* m, const float* d_grid, int32_t N, const double* d_ranges,
+                               const double* d_estPose, const double* d_rv, const double* d_tw,
+                               const double* d_uniforms, double* d_outPose, double* d_outConf, int32_t* d_outIdx,
+                               int32_t* d_status, void* d_workspace, size_t workspaceBytes,
+                               const slam_match_debug* debug, void* stream) {
+  if (!m || !d_grid || !d_ranges || !d_estPose || !d_rv || !d_outPose || !d_outConf || !d_outIdx || !d_status)
+    return fail(SLAM_E_BADARG, "slam_match_scan: null argument");
+  if (N <= 0) return 0;
+  if (!d_workspace || workspaceBytes < m->workspaceBytes) return fail(SLAM_E_BADARG, "slam_match_scan: workspace too small");
+  MatchParams P = m->P;
+  P.N = N;
+  P.grid = d_grid; P.ranges = d_ranges; P.estPose = d_estPose; P.rv = d_rv; P.tw = d_tw; P.uniforms = d_uniforms;
+  P.outPose = d_outPose; P.outConf = d_outConf; P.outIdx = d_outIdx; P.status = d_status;
+  P.scratch = (unsigned char*)align_up((size_t)d_workspace, 256);
+  for (int s = 0; s < 2; ++s) {
+    P.dbgProb[s] = debug ? debug->d_prob[s] : nullptr;
+    P.dbgDims[s] = debug ? debug->d_probDims[s] : nullptr;
+    P.dbgVol[s] = debug ? debug->d_vol[s] : nullptr;
+    if (P.dbgProb[s] && !P.dbgDims[s]) return fail(SLAM_E_BADARG, "d_prob needs d_probDims");
+  }
+  static bool attrSet = false;
+  if (!attrSet) {
+    SLAM_CUDA(cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attrSet = true;
+  }
+  const int grid = std::min(N, m->numCtas);
+  match_kernel<<<grid, NT, m->smemBytes, (cudaStream_t)stream>>>(P);
+  SLAM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int slam_motion_priors(int32_t N, int32_t nHalf, double coef, const double* d_phi, const int32_t* d_hasPhi,
+                                  double* d_tw, void* stream) {
+  if (N <= 0) return 0;
+  if (!d_phi || !d_hasPhi || !d_tw || nHalf < 0) return fail(SLAM_E_BADARG, "slam_motion_priors: bad argument");
+  const long long total = (long long)N * (2 * nHalf + 1) * (2 * nHalf + 1);
+  const int bt = 256;
+  priors_kernel<<<(unsigned)((total + bt - 1) / bt), bt, 0, (cudaStream_t)stream>>>(N, nHalf, coef, d_phi, d_hasPhi, d_tw);
+  SLAM_CUDA(cudaGetLastError());
+  return 0;
+}

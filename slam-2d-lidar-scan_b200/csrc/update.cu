@@ -1,0 +1,225 @@
+// OccupancyGrid.updateOccupancyGrid for a batch of particles (Utils/OccupancyGrid.py:127-152), sm_100a.
+//
+// The reference walks the 180 beams; for beam i it takes the pre-binned list of lidar-local cells whose bearing
+// sector is (start + offset + i) % numSpokes and applies
+//     total[empty] += 1                      empty:  range_i < maxRange and r < range_i - wall/2
+//     visited[hit] += 2; total[hit] += 2     hit:    range_i - wall/2 < r < range_i + wall/2
+// where the map index of a local cell is rint((pose + local - mapLim0)/unit) and numpy's fancy `+=` applies
+// once per distinct map cell per statement.
+//
+// Here the loop is inverted (owner computes, no atomics): sectors of distinct beams are disjoint, so a local
+// cell belongs to at most one beam.  A per-particle preparation pass evaluates the float64 index maps of the
+// L local columns / rows; when both are pure shifts (always true for poses emitted by the matcher, which sit
+// on the lattice) every local cell owns exactly one map cell and the fast kernel runs; otherwise (pose exactly
+// half a cell off the lattice, where rint's half-to-even collapses neighbours) the general map-cell-owned
+// kernel reproduces the per-statement union semantics.
+#include "common.cuh"
+
+namespace slam {
+
+struct UpdParams {
+  int G, pitch, K, L, numSpokes, start, N;
+  double unit, mapX0, mapY0, maxRange, wallHalf;
+  const short* sector;
+  const double *radius, *axis, *ranges, *pose;
+  float* grid;
+  int4* prep;   // per particle: (shiftX, shiftY, spokeOffset, flags) flags: bit0 pure shift
+  int* slow;    // slow[0] = number of particles needing the general path, slow[1..] = their indices
+  int* status;
+};
+
+constexpr int UPD_PURE = 1;
+
+// one warp per particle: float64 index maps of the local lattice (OccupancyGrid.py:144-145 via :102-106)
+__global__ void update_prep_kernel(UpdParams P) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= P.N) return;
+  const double x = P.pose[3 * warp], y = P.pose[3 * warp + 1], th = P.pose[3 * warp + 2];
+  const int sx = (int)rint(ddiv(dsub(dadd(x, P.axis[0]), P.mapX0), P.unit));
+  const int sy = (int)rint(ddiv(dsub(dadd(y, P.axis[0]), P.mapY0), P.unit));
+  bool pure = true;
+  for (int l = lane; l < P.L; l += 32) {
+    const int ix = (int)rint(ddiv(dsub(dadd(x, P.axis[l]), P.mapX0), P.unit));
+    const int iy = (int)rint(ddiv(dsub(dadd(y, P.axis[l]), P.mapY0), P.unit));
+    if (ix != sx + l || iy != sy + l) pure = false;
+  }
+  pure = __all_sync(0xffffffffu, pure);
+  if (lane == 0) {
+    // spokesOffsetIdxByTheta = int(rint(theta / (2*pi) * numSpokes))  (:131)
+    const int off = (int)rint(dmul(ddiv(th, 6.283185307179586), (double)P.numSpokes));
+    P.prep[warp] = make_int4(sx, sy, off, pure ? UPD_PURE : 0);
+    if (!pure) P.slow[1 + atomicAdd(&P.slow[0], 1)] = warp;
+  }
+}
+
+__device__ __forceinline__ int beam_of(int sector, int start, int off, int numSpokes) {
+  int b = (sector - start - off) % numSpokes;    // inverse of spokeIdx = (start + off + i) % numSpokes (:134)
+  return b < 0 ? b + numSpokes : b;
+}
+
+// Fast path: thread owns local cells; loops over a chunk of particles with the table entry in registers.
+constexpr int UPD_CHUNK = 32;
+__global__ void __launch_bounds__(256) update_fast_kernel(UpdParams P) {
+  extern __shared__ double s_ranges[];
+  __shared__ int4 s_prep[UPD_CHUNK];
+  const int p0 = blockIdx.y * UPD_CHUNK;
+  const int np = min(UPD_CHUNK, P.N - p0);
+  for (int k = threadIdx.x; k < P.K; k += blockDim.x) s_ranges[k] = P.ranges[k];
+  if (threadIdx.x < np) s_prep[threadIdx.x] = P.prep[p0 + threadIdx.x];
+  __syncthreads();
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= P.L * P.L) return;
+  const int ly = cell / P.L, lx = cell - ly * P.L;
+  const int sec = P.sector[cell];
+  const double r = P.radius[cell];
+  const size_t gstride = (size_t)P.G * P.pitch;
+  int bad = 0;
+  for (int q = 0; q < np; ++q) {
+    const int4 pr = s_prep[q];
+    if (!(pr.w & UPD_PURE)) continue;
+    const int beam = beam_of(sec, P.start, pr.z, P.numSpokes);
+    if (beam >= P.K) continue;
+    const double rm = s_ranges[beam];
+    const double lo = dsub(rm, P.wallHalf), hi = dadd(rm, P.wallHalf);
+    const bool empty = rm < P.maxRange && r < lo;
+    const bool hit = r > lo && r < hi;
+    if (!(empty || hit)) continue;
+    const int jx = pr.x + lx, jy = pr.y + ly;
+    if (jx < 0 || jy < 0 || jx >= P.G || jy >= P.G) { bad = 1; continue; }
+    float2* c = (float2*)P.grid + (size_t)(p0 + q) * gstride + (size_t)jy * P.pitch + jx;
+    float2 v = *c;
+    if (empty) v.y += 1.f;
+    if (hit) { v.x += 2.f; v.y += 2.f; }
+    *c = v;
+  }
+  if (bad) {
+    // conservative: flag every particle of the chunk that was written out of bounds is not tracked per particle
+    for (int q = 0; q < np; ++q) {
+      const int4 pr = s_prep[q];
+      const int jx = pr.x + lx, jy = pr.y + ly;
+      if (jx < 0 || jy < 0 || jx >= P.G || jy >= P.G) atomicOr(&P.status[p0 + q], SLAM_ST_SCAN_OUTSIDE_MAP);
+    }
+  }
+}
+
+// General path (non-pure index maps): loops over the flagged particles; thread owns a MAP cell of the patch's
+// bounding box and tests the <= 3x3 local cells that can round onto it; union within a beam, sum across beams.
+__device__ void update_general_one(const UpdParams& P, int p, int* mx, int* my);
+
+__global__ void __launch_bounds__(256) update_general_kernel(UpdParams P) {
+  extern __shared__ int s_maps[];   // mx[L], my[L]
+  const int count = P.slow[0];
+  for (int q = 0; q < count; ++q) {
+    update_general_one(P, P.slow[1 + q], s_maps, s_maps + P.L);
+    __syncthreads();
+  }
+}
+
+__device__ void update_general_one(const UpdParams& P, int p, int* mx, int* my) {
+  const int4 pr = P.prep[p];
+  const double x = P.pose[3 * p], y = P.pose[3 * p + 1];
+  for (int l = threadIdx.x; l < P.L; l += blockDim.x) {
+    mx[l] = (int)rint(ddiv(dsub(dadd(x, P.axis[l]), P.mapX0), P.unit));
+    my[l] = (int)rint(ddiv(dsub(dadd(y, P.axis[l]), P.mapY0), P.unit));
+  }
+  __syncthreads();
+  const int side = P.L + 2;   // bounding box in shifted map coordinates: [shift-1, shift+L]
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= side * side) return;
+  const int cy = cell / side, cx = cell - cy * side;
+  const int jx = pr.x - 1 + cx, jy = pr.y - 1 + cy;
+  int nb = 0;
+  int beams[9];
+  unsigned char flag[9];   // bit0 empty, bit1 hit
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int ly = cy - 1 + dy;
+    if (ly < 0 || ly >= P.L || my[ly] != jy) continue;
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int lx = cx - 1 + dx;
+      if (lx < 0 || lx >= P.L || mx[lx] != jx) continue;
+      const int lc = ly * P.L + lx;
+      const int beam = beam_of(P.sector[lc], P.start, pr.z, P.numSpokes);
+      if (beam >= P.K) continue;
+      const double rm = P.ranges[beam], r = P.radius[lc];
+      const double lo = dsub(rm, P.wallHalf), hi = dadd(rm, P.wallHalf);
+      const unsigned char f = ((rm < P.maxRange && r < lo) ? 1 : 0) | ((r > lo && r < hi) ? 2 : 0);
+      if (!f) continue;
+      int k = 0;
+      for (; k < nb; ++k)
+        if (beams[k] == beam) break;
+      if (k == nb) { beams[nb] = beam; flag[nb] = 0; ++nb; }
+      flag[k] |= f;
+    }
+  }
+  if (nb == 0) return;
+  float dv = 0.f, dt = 0.f;
+  for (int k = 0; k < nb; ++k) {
+    if (flag[k] & 1) dt += 1.f;
+    if (flag[k] & 2) { dv += 2.f; dt += 2.f; }
+  }
+  if (jx < 0 || jy < 0 || jx >= P.G || jy >= P.G) { atomicOr(&P.status[p], SLAM_ST_SCAN_OUTSIDE_MAP); return; }
+  float2* c = (float2*)P.grid + (size_t)p * P.G * P.pitch + (size_t)jy * P.pitch + jx;
+  float2 v = *c;
+  v.x += dv; v.y += dt;
+  *c = v;
+}
+
+__global__ void grid_init_kernel(float4* g, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const float4 v = make_float4(1.f, 2.f, 1.f, 2.f);
+  for (; i < n4; i += stride) g[i] = v;
+}
+
+}  // namespace slam
+
+using namespace slam;
+
+extern "C" int slam_grid_init(const slam_geometry* g, float* d_grid, int32_t N, void* stream) {
+  if (!g || !d_grid || N < 0) return fail(SLAM_E_BADARG, "slam_grid_init: bad argument");
+  const size_t n4 = (size_t)N * g->G * g->pitch / 2;
+  if (n4 == 0) return 0;
+  grid_init_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>((float4*)d_grid, n4);
+  SLAM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int4* g_prep = nullptr;   // per-process scratch for the preparation pass (grown on demand)
+static int* g_slow = nullptr;
+static int g_prepCap = 0;
+
+extern "C" int slam_update_grid(const slam_geometry* g, float* d_grid, int32_t N, const double* d_ranges,
+                                const double* d_pose, int32_t* d_status, void* stream) {
+  if (!g || !d_grid || !d_ranges || !d_pose || !d_status) return fail(SLAM_E_BADARG, "slam_update_grid: null argument");
+  if (N <= 0) return 0;
+  if (g->K > SLAM_MAX_BEAMS) return fail(SLAM_E_UNSUPPORTED, "too many beams");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N > g_prepCap) {
+    if (g_prep) cudaFree(g_prep);
+    if (g_slow) cudaFree(g_slow);
+    g_prep = nullptr; g_slow = nullptr; g_prepCap = 0;
+    SLAM_CUDA(cudaMalloc(&g_prep, (size_t)N * sizeof(int4)));
+    SLAM_CUDA(cudaMalloc(&g_slow, ((size_t)N + 1) * sizeof(int)));
+    g_prepCap = N;
+  }
+  SLAM_CUDA(cudaMemsetAsync(g_slow, 0, sizeof(int), st));
+  UpdParams P;
+  P.G = g->G; P.pitch = g->pitch; P.K = g->K; P.L = g->L; P.numSpokes = g->numSpokes; P.start = g->spokesStartIdx; P.N = N;
+  P.unit = g->unit; P.mapX0 = g->mapX0; P.mapY0 = g->mapY0; P.maxRange = g->maxRange; P.wallHalf = g->wallHalf;
+  P.sector = g->d_sector; P.radius = g->d_radius; P.axis = g->d_localAxis; P.ranges = d_ranges; P.pose = d_pose;
+  P.grid = d_grid; P.prep = g_prep; P.slow = g_slow; P.status = d_status;
+  update_prep_kernel<<<(N * 32 + 255) / 256, 256, 0, st>>>(P);
+  SLAM_CUDA(cudaGetLastError());
+  {
+    dim3 grid((g->L * g->L + 255) / 256, (N + UPD_CHUNK - 1) / UPD_CHUNK);
+    update_fast_kernel<<<grid, 256, g->K * sizeof(double), st>>>(P);
+    SLAM_CUDA(cudaGetLastError());
+  }
+  {
+    const int side = g->L + 2;
+    dim3 grid((side * side + 255) / 256, 1);
+    update_general_kernel<<<grid, 256, 2 * g->L * sizeof(int), st>>>(P);
+    SLAM_CUDA(cudaGetLastError());
+  }
+  return 0;
+}

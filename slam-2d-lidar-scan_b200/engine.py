@@ -1,0 +1,165 @@
+"""Batched device engine behind the reference-shaped classes: one call = one kernel launch over N particles.
+
+Host code only prepares constants with the reference's own Python/numpy expressions (so they are bit-identical
+to what the reference would compute) and moves small buffers; all per-particle arithmetic runs in the sm_100a
+kernels of csrc/ through the C ABI (include/slam2d_b200.h).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def gaussian_taps(sigma, truncate=4.0):
+    """Taps scipy.ndimage.gaussian_filter1d would use for `sigma` (mode/truncate defaults), centre at [radius]."""
+    sd = float(sigma)
+    radius = int(truncate * sd + 0.5)
+    sigma2 = sigma * sigma
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / sigma2 * x ** 2)
+    phi = phi / phi.sum()
+    return phi[::-1].copy(), radius
+
+
+def raise_for_status(bits):
+    if bits & nat.ST_WINDOW_OUTSIDE_MAP:
+        raise IndexError("search window leaves the pre-sized map (the reference would expand it; pre-size the map)")
+    if bits & nat.ST_SCAN_OUTSIDE_MAP:
+        raise IndexError("scan update touches cells outside the pre-sized map")
+    if bits & nat.ST_INDEX_OUT_OF_FIELD:
+        raise IndexError("scan point outside the likelihood-field window")
+    if bits & nat.ST_NAN_SCORE:
+        raise ValueError("probabilities contain NaN")
+    if bits & nat.ST_HEADING_MISSING:
+        raise TypeError("unsupported operand type(s) for +: 'NoneType' and 'float' (prevMatchedMovingTheta is None)")
+
+
+class MatcherEngine:
+    """Device plan for ScanMatcher.matchScan (Utils/ScanMatcher_OGBased.py:47-79) on a given geometry."""
+
+    def __init__(self, geom, searchRadius, searchHalfRad, scanSigmaInNumGrid, moveRSigma, maxMoveDeviation, turnSigma,
+                 missMatchProbAtCoarse, coarseFactor, fineSearchHalfRad=None):
+        self.geom = geom
+        self.searchRadius, self.searchHalfRad = searchRadius, searchHalfRad
+        self.scanSigmaInNumGrid, self.coarseFactor = scanSigmaInNumGrid, coarseFactor
+        self.moveRSigma, self.turnSigma = moveRSigma, turnSigma
+        self.missMatchProbAtCoarse, self.maxMoveDeviation = missMatchProbAtCoarse, maxMoveDeviation
+        u = geom.unitGridSize
+        self.coarseStep = coarseFactor * u                                   # :54
+        coarseSigma = scanSigmaInNumGrid / coarseFactor                      # :55
+        fineMiss = missMatchProbAtCoarse ** (2 / coarseFactor)               # :69
+        self.windowRadius = 1.1 * geom.lidarMaxRange + searchRadius          # :21
+        fineHalf = searchHalfRad if fineSearchHalfRad is None else fineSearchHalfRad   # :68 (extension: keyword)
+        self._keep = []
+        desc = nat.MatcherDesc()
+        desc.windowRadius = self.windowRadius
+        self.stageInfo = []
+        for st, ul, sigma, miss, radius, half in (
+                (desc.coarse, self.coarseStep, coarseSigma, missMatchProbAtCoarse, searchRadius, searchHalfRad),
+                (desc.fine, u, scanSigmaInNumGrid, fineMiss, self.coarseStep, fineHalf)):
+            taps, r = gaussian_taps(sigma)
+            if r < 1 or r > nat.MAX_BLUR_RADIUS:
+                raise NotImplementedError("blur radius %d outside 1..%d" % (r, nat.MAX_BLUR_RADIUS))
+            thetas = np.arange(-half, half + geom.angularStep, geom.angularStep)          # :114
+            cosT = np.array([np.cos(t) for t in thetas])                                 # rotate() gets scalars (:169)
+            sinT = np.array([np.sin(t) for t in thetas])
+            st.unitLength, st.logMiss, st.blurRadius = ul, math.log(miss), r
+            for i, t in enumerate(taps):
+                st.blurW[i] = t
+            st.nHalf = int(radius / ul)                                                   # :94
+            st.nTheta = len(thetas)
+            for name, arr in (("h_thetas", thetas), ("h_cos", cosT), ("h_sin", sinT)):
+                arr = np.ascontiguousarray(arr, dtype=np.float64)
+                self._keep.append(arr)
+                setattr(st, name, arr.ctypes.data_as(nat.c_double_p))
+            self.stageInfo.append(dict(unitLength=ul, nHalf=st.nHalf, thetas=thetas, radius=r))
+        # every gather must stay inside the window: |point - pose| < maxRange, offsets <= nHalf cells
+        margin = self.windowRadius - geom.lidarMaxRange
+        if margin < self.stageInfo[0]["nHalf"] * self.coarseStep or margin < self.stageInfo[1]["nHalf"] * u:
+            raise ValueError("search radius exceeds the window margin")
+        h = C.c_void_p()
+        with torch.cuda.device(geom.device):
+            nat.check(nat.lib.slam_matcher_create(C.byref(geom.c), C.byref(desc), C.byref(h)))
+        self.handle = h
+        self.nOffC = 2 * self.stageInfo[0]["nHalf"] + 1
+        self.workspace = torch.empty(nat.lib.slam_matcher_workspace_bytes(h), dtype=torch.uint8, device=geom.device)
+        self.zeroRv = torch.zeros(self.nOffC * self.nOffC, dtype=torch.float64, device=geom.device)
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h and nat is not None:
+            nat.lib.slam_matcher_destroy(h)
+
+    # -- priors of the coarse stage (:95-110), host side, reference expressions
+    def offset_axis(self, stage=0):
+        n = self.stageInfo[stage]["nHalf"]
+        return np.arange(-n, n + 1)
+
+    def radial_prior(self, estMovingDist):
+        ax = self.offset_axis(0)
+        xv, yv = np.meshgrid(ax, ax)
+        ul = self.coarseStep
+        d = np.sqrt((xv * ul) ** 2 + (yv * ul) ** 2)
+        rv = - (1 / (2 * self.moveRSigma ** 2)) * (d - estMovingDist) ** 2                # :101
+        rv[np.abs(d - estMovingDist) > self.maxMoveDeviation] = -100                      # :102-103
+        return rv
+
+    def heading_prior(self, estMovingTheta):
+        ax = self.offset_axis(0)
+        xv, yv = np.meshgrid(ax, ax)
+        if estMovingTheta is None:
+            return np.zeros(xv.shape)                                                     # :110
+        dist = np.sqrt(np.square(xv) + np.square(yv))
+        dist[dist == 0] = 0.0001
+        with np.errstate(invalid='ignore'):
+            ang = np.arccos((xv * math.cos(estMovingTheta) + yv * math.sin(estMovingTheta)) / dist)   # :107
+        return -1 / (2 * self.turnSigma ** 2) * np.square(ang)                            # :108
+
+    @property
+    def heading_coef(self):
+        return -1 / (2 * self.turnSigma ** 2)
+
+    def debug_buffers(self, n):
+        dev = self.geom.device
+        dbg = nat.MatchDebug()
+        bufs = {}
+        for s in range(2):
+            side = nat.lib.slam_matcher_field_side(self.handle, s)
+            poses = nat.lib.slam_matcher_num_poses(self.handle, s)
+            bufs["prob%d" % s] = torch.zeros((n, side, side), dtype=torch.float64, device=dev)
+            bufs["dims%d" % s] = torch.zeros((n, 2), dtype=torch.int32, device=dev)
+            bufs["vol%d" % s] = torch.zeros((n, poses), dtype=torch.float64, device=dev)
+            dbg.d_prob[s] = bufs["prob%d" % s].data_ptr()
+            dbg.d_probDims[s] = bufs["dims%d" % s].data_ptr()
+            dbg.d_vol[s] = bufs["vol%d" % s].data_ptr()
+        return dbg, bufs
+
+    def match(self, grids, n, d_ranges, d_estPose, d_rv, d_tw, d_uniforms, d_outPose, d_outConf, d_outIdx, d_status,
+              debug=None):
+        """slam_match_scan on the current stream.  All arguments are device tensors (or None)."""
+        dev = self.geom.device
+        nat.check(nat.lib.slam_match_scan(
+            self.handle, grids.data_ptr(), n, d_ranges.data_ptr(), d_estPose.data_ptr(), d_rv.data_ptr(), _ptr(d_tw),
+            _ptr(d_uniforms), d_outPose.data_ptr(), d_outConf.data_ptr(), d_outIdx.data_ptr(), d_status.data_ptr(),
+            self.workspace.data_ptr(), self.workspace.numel(), C.byref(debug) if debug is not None else None,
+            _stream(dev)))
+
+    def volume_shape(self, stage):
+        n = 2 * self.stageInfo[stage]["nHalf"] + 1
+        return (len(self.stageInfo[stage]["thetas"]), n, n)
+
+
+def update_grids(geom, grids, n, d_ranges, d_pose, d_status):
+    nat.check(nat.lib.slam_update_grid(geom.c, grids.data_ptr(), n, d_ranges.data_ptr(), d_pose.data_ptr(),
+                                       d_status.data_ptr(), _stream(geom.device)))

@@ -1,0 +1,269 @@
+"""ParticleFilter / Particle with the reference's surface (Algorithm/FastSlam.py:10-150) over a device-resident
+batch of N particles, plus the FastSLAM facade (``step``) named by BASELINE.json.
+
+State lives in torch tensors on one GPU: lattices [N][G][pitch][2] float32, poses/headings/weights float64.
+``updateParticles`` is five kernel launches for all N particles (propose, priors, fused match, finish, map
+update); the reference's Python loop over particles (FastSlam.py:25-27) is gone.
+
+RNG contract: the reference draws from numpy's global legacy RandomState -- one double per particle per
+``matchScan`` (coarse sampling, in particle order) and N doubles per ``resample``.  The same draws are made
+here on the host, so a run seeded with ``np.random.seed`` consumes the identical stream.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .engine import MatcherEngine, raise_for_status, update_grids, _stream
+from .geometry import LidarGeometry
+from .grid import OccupancyGrid
+from .matcher import ScanMatcher
+
+
+class Particle:
+    """View of slot ``i`` of a ParticleFilter (Algorithm/FastSlam.py:64-150)."""
+
+    def __init__(self, pf, i):
+        self._pf, self._i = pf, i
+        self.og = OccupancyGrid(*pf.geom.args, _geometry=pf.geom, _grids=pf.grids, _slot=i)
+        self.sm = ScanMatcher(self.og, *pf.smParameters, _engine=pf.engine)
+
+    @property
+    def weight(self):
+        return float(self._pf.weights[self._i].item())
+
+    @weight.setter
+    def weight(self, w):
+        self._pf.weights[self._i] = float(w)
+
+    @property
+    def xTrajectory(self):
+        return [float(t[self._i, 0].item()) for t in self._pf._traj]
+
+    @property
+    def yTrajectory(self):
+        return [float(t[self._i, 1].item()) for t in self._pf._traj]
+
+    @property
+    def prevMatchedReading(self):
+        x, y, th = self._pf.prevMatched[self._i].cpu().tolist()
+        raw = self._pf._prevRaw[self._i]
+        return {'x': x, 'y': y, 'theta': th, 'range': raw['range'] if raw else None}
+
+    @property
+    def prevRawReading(self):
+        return self._pf._prevRaw[self._i]
+
+    @property
+    def prevMatchedMovingTheta(self):
+        if not int(self._pf.hasHeading[self._i].item()):
+            return None
+        return float(self._pf.prevHeading[self._i].item())
+
+    def update(self, reading, count):
+        """Particle.update (FastSlam.py:122-135) for this particle only."""
+        self._pf._update(self._i, self._i + 1, reading, count)
+        self._pf._rawUniform = False
+
+    def plotParticle(self):
+        raise NotImplementedError("plotting is out of scope")
+
+
+class ParticleFilter:
+    def __init__(self, numParticles, ogParameters, smParameters, *, device=None, geometry=None, engine=None):
+        self.numParticles = numParticles
+        (mapX, mapY, initXY, unit, lidarFOV, lidarMaxRange, numSamplesPerRev, wallThickness) = ogParameters   # :66
+        self.ogParameters, self.smParameters = list(ogParameters), list(smParameters)
+        self.geom = geometry or LidarGeometry(mapX, mapY, initXY, unit, lidarFOV, numSamplesPerRev, lidarMaxRange,
+                                              wallThickness, device=device)
+        self.engine = engine or MatcherEngine(self.geom, *smParameters)
+        self.step = 0                        # unused int attribute of the reference (FastSlam.py:15)
+        self.prevMatchedReading = None       # idem (:16-18)
+        self.prevRawReading = None
+        self.particlesTrajectory = []
+        n, dev = numParticles, self.geom.device
+        f64 = dict(dtype=torch.float64, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.grids = self.geom.new_grids(n)
+        self.prevMatched = torch.zeros((n, 3), **f64)
+        self.prevHeading = torch.zeros(n, **f64)
+        self.hasHeading = torch.zeros(n, **i32)
+        self.weights = torch.ones(n, **f64)                                  # Particle.weight = 1 (:75)
+        self.status = torch.zeros(n, **i32)
+        self._est = torch.zeros((n, 3), **f64)
+        self._phi = torch.zeros(n, **f64)
+        self._hasPhi = torch.zeros(n, **i32)
+        self._matched = torch.zeros((n, 3), **f64)
+        self._conf = torch.zeros(n, **f64)
+        self._idx = torch.zeros((n, 6), **i32)
+        n2 = self.engine.nOffC ** 2
+        self._tw = torch.zeros((n, n2), **f64)
+        self._rv = torch.zeros(n2, **f64)
+        K = self.geom.numSamplesPerRev
+        self._stage_h = torch.zeros(K + n + n2, dtype=torch.float64).pin_memory()   # ranges | uniforms | rv
+        self._stage_d = torch.zeros(K + n + n2, **f64)
+        self._stage_ev = torch.cuda.Event()
+        self._stage_busy = False
+        self._out = torch.zeros(4, **f64)
+        self._cdf = torch.zeros(n, **f64)
+        self._ridx = torch.zeros(n, **i32)
+        self._traj = []
+        self._prevRaw = [None] * n
+        self._prevRawHeading = [None] * n
+        self._rawUniform = True
+        self._particles = None
+        self.lastVariance = None
+        self.lastResampleIdx = None
+
+    # ---- reference surface
+    @property
+    def particles(self):
+        if self._particles is None:
+            self._particles = [Particle(self, i) for i in range(self.numParticles)]
+        return self._particles
+
+    def updateParticles(self, reading, count):
+        """FastSlam.py:25-27 -- all particles in one batch."""
+        if self._rawUniform:
+            self._update(0, self.numParticles, reading, count)
+        else:
+            for i in range(self.numParticles):
+                self._update(i, i + 1, reading, count)
+
+    def normalizeWeights(self):
+        self._normalize()
+
+    def weightUnbalanced(self):
+        """Normalise, then the reference's variance trigger (FastSlam.py:30-41).  Synchronises (returns a bool)."""
+        self._normalize()
+        out = torch.cat([self._out[:2], self.status.max().to(torch.float64).view(1)]).cpu()
+        raise_for_status(int(out[2].item()))
+        self.lastVariance = float(out[0].item())
+        return bool(out[1].item() != 0.0)
+
+    def resample(self):
+        """np.random.choice(arange(N), N, p=weights) + deep copy of the chosen particles (FastSlam.py:50-62)."""
+        n, dev = self.numParticles, self.geom.device
+        u = torch.from_numpy(np.random.random_sample(n)).to(dev)
+        st = _stream(dev)
+        nat.check(nat.lib.slam_resample_indices(n, self.weights.data_ptr(), u.data_ptr(), self._cdf.data_ptr(),
+                                                self._ridx.data_ptr(), st))
+        newGrids = torch.empty_like(self.grids)
+        newPrev = torch.empty_like(self.prevMatched)
+        nat.check(nat.lib.slam_gather_particles(self.geom.c, n, self._ridx.data_ptr(), self.grids.data_ptr(),
+                                                newGrids.data_ptr(), self.prevMatched.data_ptr(), newPrev.data_ptr(),
+                                                3, self.weights.data_ptr(), st))
+        idx = self._ridx.to(torch.int64)
+        self.grids.copy_(newGrids)                 # keep the storage the Particle views alias
+        self.prevMatched.copy_(newPrev)
+        del newGrids
+        self.prevHeading = self.prevHeading.index_select(0, idx).contiguous()
+        self.hasHeading = self.hasHeading.index_select(0, idx).contiguous()
+        self._traj = [t.index_select(0, idx) for t in self._traj]
+        hidx = idx.cpu().tolist()
+        self._prevRaw = [self._prevRaw[i] for i in hidx]
+        self._prevRawHeading = [self._prevRawHeading[i] for i in hidx]
+        self.lastResampleIdx = np.asarray(hidx)
+
+    # ---- device step
+    def _normalize(self):
+        nat.check(nat.lib.slam_normalize_weights(self.numParticles, self.weights.data_ptr(), self._out.data_ptr(),
+                                                 _stream(self.geom.device)))
+
+    def _update(self, lo, hi, reading, count):
+        """Particle.update (FastSlam.py:122-135) for particles [lo, hi)."""
+        n, dev, K = hi - lo, self.geom.device, self.geom.numSamplesPerRev
+        st = _stream(dev)
+        eng = self.engine
+        n2 = eng.nOffC ** 2
+        N = self.numParticles
+        h = self._stage_h
+        if self._stage_busy:
+            self._stage_ev.synchronize()         # previous async H2D out of the pinned staging buffer has landed
+            self._stage_busy = False
+        h[:K] = torch.from_numpy(np.asarray(reading['range'], dtype=np.float64))
+        matched = self._matched[lo:hi]
+        status = self.status[lo:hi]
+        if count == 1:
+            # matchedReading, confidence = reading, 1 (:123-125)
+            self._stage_d[:K].copy_(h[:K], non_blocking=True)
+            self._stage_ev.record(torch.cuda.current_stream(dev))
+            self._stage_busy = True
+            matched.copy_(torch.tensor([reading['x'], reading['y'], reading['theta']], dtype=torch.float64))
+            self.hasHeading[lo:hi] = 0
+            self.prevMatched[lo:hi] = matched
+            newRawHeading = None
+        else:
+            raw, prevRaw, prevRawHeading = reading, self._prevRaw[lo], self._prevRawHeading[lo]
+            dx, dy = raw['x'] - prevRaw['x'], raw['y'] - prevRaw['y']
+            estMovingDist = math.sqrt(dx ** 2 + dy ** 2)                                     # :82
+            rawMove = math.sqrt((raw['x'] - prevRaw['x']) ** 2 + (raw['y'] - prevRaw['y']) ** 2)   # :86
+            mode, rawTurn, newRawHeading = 0, 0.0, None
+            if rawMove > 0.3:                                                                # :88-101
+                newRawHeading = math.acos(dx / rawMove) if dy > 0 else -math.acos(dx / rawMove)
+                if prevRawHeading is not None:
+                    mode, rawTurn = 1, newRawHeading - prevRawHeading
+            h[K:K + n] = torch.from_numpy(np.random.random_sample(n))       # one draw per matchScan, particle order
+            h[K + N:K + N + n2] = torch.from_numpy(eng.radial_prior(estMovingDist).reshape(-1))
+            self._stage_d.copy_(h, non_blocking=True)
+            self._stage_ev.record(torch.cuda.current_stream(dev))
+            self._stage_busy = True
+            d_u = self._stage_d[K:K + n]
+            d_rv = self._stage_d[K + N:K + N + n2]
+            nat.check(nat.lib.slam_propose_poses(
+                n, self.prevMatched[lo:hi].data_ptr(), raw['theta'], prevRaw['theta'], mode, rawTurn,
+                self.prevHeading[lo:hi].data_ptr(), self.hasHeading[lo:hi].data_ptr(), self._est[lo:hi].data_ptr(),
+                self._phi[lo:hi].data_ptr(), self._hasPhi[lo:hi].data_ptr(), status.data_ptr(), st))
+            tw = None
+            if mode == 1:
+                tw = self._tw[lo:hi]
+                nat.check(nat.lib.slam_motion_priors(n, eng.stageInfo[0]["nHalf"], eng.heading_coef,
+                                                     self._phi[lo:hi].data_ptr(), self._hasPhi[lo:hi].data_ptr(),
+                                                     tw.data_ptr(), st))
+            eng.match(self.grids[lo:hi], n, self._stage_d[:K], self._est[lo:hi], d_rv, tw, d_u, matched,
+                      self._conf[lo:hi], self._idx[lo:hi], status)
+            nat.check(nat.lib.slam_finish_step(n, matched.data_ptr(), self._conf[lo:hi].data_ptr(),
+                                               self.prevMatched[lo:hi].data_ptr(), self.prevHeading[lo:hi].data_ptr(),
+                                               self.hasHeading[lo:hi].data_ptr(), self.weights[lo:hi].data_ptr(), st))
+        if n == N:
+            self._traj.append(matched[:, :2].clone())
+        else:
+            if not self._traj or self._traj[-1].shape[0] != N or getattr(self, "_trajCount", None) != count:
+                self._traj.append(torch.zeros((N, 2), dtype=torch.float64, device=dev))
+            self._traj[-1][lo:hi] = matched[:, :2]
+        self._trajCount = count
+        update_grids(self.geom, self.grids[lo:hi], n, self._stage_d[:K], matched, status)    # :133
+        if n == N:
+            self._prevRaw = [reading] * N
+            self._prevRawHeading = [newRawHeading] * N
+        else:
+            for i in range(lo, hi):
+                self._prevRaw[i] = reading
+                self._prevRawHeading[i] = newRawHeading
+
+    # ---- conveniences beyond the reference
+    def poses(self):
+        """[N][3] matched poses of the last step (host numpy)."""
+        return self.prevMatched.cpu().numpy()
+
+    def best_particle(self):
+        return int(torch.argmax(self.weights).item())
+
+
+class FastSLAM:
+    """Facade named by BASELINE.json: ``step(reading)`` = the loop body of FastSlam.py:159-162."""
+
+    def __init__(self, numParticles, ogParameters, smParameters, *, device=None):
+        self.pf = ParticleFilter(numParticles, ogParameters, smParameters, device=device)
+        self.count = 0
+        self.resampled = []
+
+    def step(self, reading):
+        self.count += 1
+        self.pf.updateParticles(reading, self.count)
+        fired = self.pf.weightUnbalanced()
+        if fired:
+            self.pf.resample()
+        self.resampled.append(fired)
+        return fired
