@@ -874,7 +874,13 @@ extern "C" int slam_match_scan(slam_matcher* m, const float* d_grid, int32_t N, 
   }
   static bool attrSet = false;
   if (!attrSet) {
-    SLAM_CUDA(cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int dev = 0, optin = 0;
+    SLAM_CUDA(cudaGetDevice(&dev));
+    SLAM_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cudaFuncAttributes fa;
+    SLAM_CUDA(cudaFuncGetAttributes(&fa, match_kernel));
+    SLAM_CUDA(cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   optin - (int)fa.sharedSizeBytes));
     attrSet = true;
   }
   const int grid = std::min(N, m->numCtas);
