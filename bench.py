@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the scan-match / FastSLAM hot path (BASELINE.json metric: particle-scans/s + HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c2|c5]
+
+A "step" is one FastSLAM step over the rank's particles: odometry proposal, priors, fused coarse+fine scan match,
+heading/weight update, map update, weight normalisation (+ the all-gather when N > 1).  Weak scaling: every GPU
+holds the workload's particle count (c3: 1024 particles, 1001x1001 lattices @0.05 m, 180 beams, 10 440 poses).
+
+  value   whole-job particle-scans/s with the step's inputs already resident in HBM (pre-staged), CUDA-event timed
+  e2e     the same through the public API (ParticleFilter.updateParticles + weightUnbalanced) with HOST readings:
+          per step one pinned H2D copy (ranges | uniforms | radial prior) and a D2H read of (variance, trigger, status)
+  roofline  fused match kernel: N * B_match algorithmic bytes / its mean CUDA-event duration, vs the measured HBM peak
+  cpu_baseline  the oracle port of the reference's numpy path on the host cores (rank 0, N=1, bounded sample)
+
+--impl reference times the oracle port (the reference is pure Python and is not present on the GPU box) on all
+host cores for the same workload/metric.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "particle-scans/s (180-beam scan matched + mapped per particle)"
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def _cpu_worker(args):
+    """One process = one particle of the oracle (the reference's numpy path restated), timed over `steps` steps."""
+    workload, steps, seed = args
+    from oracle import slam_oracle as O
+    spec = importlib_pkg().synthetic.config(workload)
+    scene = importlib_pkg().synthetic.make_scene(seed=0, steps=steps + 1, K=spec["K"], fov=spec["og"][4],
+                                                 unit=spec["og"][3])
+    np.random.seed(seed)
+    p = O.Particle(spec["og"], spec["sm"])
+    for fr in scene["warm"]:
+        p.og.updateOccupancyGrid(fr)
+    p.update(scene["frames"][0], 1)
+    t0 = time.perf_counter()
+    for count, fr in enumerate(scene["frames"][1:steps + 1], start=2):
+        p.update(fr, count)
+    return time.perf_counter() - t0
+
+
+def importlib_pkg():
+    import importlib.util
+    name = "slam_b200_synthetic_only"
+    if name in sys.modules:
+        return sys.modules[name]
+    # the synthetic scene generator is numpy-only; load it without importing the CUDA package
+
+    class _Pkg:
+        pass
+    spec = importlib.util.spec_from_file_location("slam_b200_synth", os.path.join(ROOT, "slam-2d-lidar-scan_b200",
+                                                                                   "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    pkg = _Pkg()
+    pkg.synthetic = mod
+    sys.modules[name] = pkg
+    return pkg
+
+
+def host_cores():
+    """CPUs this process may actually use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
+def cpu_baseline(workload, steps=6, procs=None):
+    procs = procs or host_cores()
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        times = pool.map(_cpu_worker, [(workload, steps, 100 + i) for i in range(procs)])
+    wall = time.perf_counter() - t0
+    slowest = max(times)
+    return dict(value=procs * steps / slowest, unit="particle-scans/s", cores=procs, kind="port",
+                sample="%d processes x 1 particle x %d steps of workload %s (oracle numpy port; %.1f s wall incl. setup)"
+                       % (procs, steps, workload, wall)), slowest
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    ge.build()
+    import slam_2d_lidar_scan_b200 as S
+    from slam_2d_lidar_scan_b200 import synthetic
+    from slam_2d_lidar_scan_b200.distributed import ShardedParticleFilter
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    spec = synthetic.config(args.workload)
+    nLocal = args.particles or spec["N"]
+    K, W = args.steps, args.warmup
+    scene = synthetic.make_scene(seed=0, steps=1 + 2 * (K + W), K=spec["K"], fov=spec["og"][4], unit=spec["og"][3])
+    np.random.seed(1234)                                  # same stream on every rank (sharding is invisible)
+    spf = ShardedParticleFilter(nLocal * world, spec["og"], spec["sm"], device=dev)
+    pf = spf.local
+    pf.keepTrajectory = False
+    # maps pre-warmed with 8 scans at true poses, identical for all particles
+    og = S.OccupancyGrid(*pf.geom.args, _geometry=pf.geom)
+    for fr in scene["warm"]:
+        og.updateOccupancyGrid(fr)
+    pf.grids.copy_(og.device_grid.unsqueeze(0).expand_as(pf.grids))
+    del og
+    frames = scene["frames"]
+    spf.updateParticles(frames[0], 1)
+    spf.weightUnbalanced()
+    count = 1
+    geomBytes = pf.grids.numel() * 4
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---- (1) inputs resident in HBM: pre-stage every step's [ranges | uniforms | rv] row
+    recs, rows = [], []
+    prevRaw, prevHead = pf._prevRaw[0], pf._prevRawHeading[0]
+    for i in range(W + K):
+        count += 1
+        fr = frames[count - 1]
+        u = np.random.random_sample(nLocal * world)[spf.lo:spf.hi]
+        row = torch.zeros_like(pf._stage_h)
+        rec = pf._prepare(fr, count, nLocal, prevRaw, prevHead, out=row, uniforms=u)
+        recs.append(rec); rows.append(row.to(dev))
+        prevRaw, prevHead = fr, rec["newRawHeading"]
+    pf._prevRaw, pf._prevRawHeading = [prevRaw] * nLocal, [prevHead] * nLocal
+    sync_all()
+    launches0 = None
+    with ClockSampler(local) as clk1:
+        for i in range(W + K):
+            if i == W:
+                sync_all()
+                pf.matchEvents = []
+                launches0 = pf.kernelLaunches
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(torch.cuda.current_stream(dev))
+            pf._launch(0, nLocal, recs[i], rows[i])
+            spf.gather_and_normalize()
+        e1.record(torch.cuda.current_stream(dev))
+        sync_all()
+    launches = pf.kernelLaunches - launches0
+    ms_dev = e0.elapsed_time(e1)
+    matchMs = [a.elapsed_time(b) for a, b in pf.matchEvents]
+    pf.matchEvents = None
+    st = int(pf.status.max().item())
+    if st:
+        raise RuntimeError("status bits %d set during the timed run" % st)
+
+    # ---- (2) end to end through the public API with host readings
+    def api_step():
+        nonlocal count
+        count += 1
+        spf.updateParticles(frames[count - 1], count)
+        return spf.weightUnbalanced()
+    for _ in range(W):
+        api_step()
+    sync_all()
+    h0, d0 = pf.h2dBytes, pf.d2hBytes
+    with ClockSampler(local) as clk2:
+        t0 = time.perf_counter()
+        for _ in range(K):
+            api_step()
+        sync_all()
+        t_e2e = time.perf_counter() - t0
+    h2d, d2h = (pf.h2dBytes - h0) // K, (pf.d2hBytes - d0) // K
+
+    # max over ranks
+    t = torch.tensor([ms_dev, t_e2e * 1e3, statistics.mean(matchMs)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e, ms_match = (float(v) for v in t.cpu())
+    if rank == 0:
+        total = nLocal * world
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = peaks.get("hbm_gbs", 6650.0)
+        eng = pf.engine
+        Wf = int(2 * eng.windowRadius / pf.geom.unitGridSize) + 1
+        bmatch = 2 * Wf * Wf * 8                       # window read once per stage, 8 B per cell
+        achieved = nLocal * bmatch / (ms_match * 1e-3) / 1e9
+        c1, c2 = clk1.summary(), clk2.summary()
+        out = {
+            "metric": METRIC, "value": total * K / (ms_dev * 1e-3), "unit": "particle-scans/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "particles_per_gpu": nLocal, "particles_total": total,
+                       "beams": spec["K"], "grid": "%dx%d @%.2f m" % (pf.geom.G, pf.geom.G, pf.geom.unitGridSize),
+                       "poses_per_scan": sum(int(np.prod(eng.volume_shape(s))) for s in (0, 1)),
+                       "parallelism": "particles sharded, %d/GPU" % nLocal,
+                       "l2": "inputs larger than L2 (%.1f GB of lattices per GPU vs 126 MB L2)" % (geomBytes / 1e9),
+                       "scene": "synthetic room seed 0 (SURVEY 8d), maps pre-warmed with 8 scans"},
+            "e2e": {"value": total * K / (ms_e2e * 1e-3), "unit": "particle-scans/s", "ms_per_step": ms_e2e / K,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "slam::match_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650",
+                         "algorithmic_bytes_per_launch": nLocal * bmatch, "ms_per_launch": ms_match,
+                         "share_of_step": ms_match / (ms_dev / K)},
+            "clocks": {"sm_mhz": c1["sm_mhz"], "sm_max_mhz": c1["sm_max_mhz"],
+                       "reasons": sorted(set(c1["reasons"]) | set(c2["reasons"])), "e2e_sm_mhz": c2["sm_mhz"]},
+        }
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"], _ = cpu_baseline(args.workload, steps=args.cpu_steps)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    K, W = args.steps, args.warmup
+    procs = host_cores()
+    spec = importlib_pkg().synthetic.config(args.workload)
+    # each bench "step" = every host core advancing one particle by `per` scan-match+map steps (bounded sample)
+    per = max(1, min(args.cpu_steps, 3))
+    times = []
+    for i in range(W + K):
+        base, slowest = cpu_baseline(args.workload, steps=per, procs=procs)
+        if i >= W:
+            times.append(slowest)
+    total_t = sum(times)
+    value = procs * per * K / total_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "particle-scans/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": total_t / K * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "beams": spec["K"], "note": "oracle numpy port of the reference's CPU path; "
+                   "the reference is pure Python and absent on the GPU box"},
+        "cpu_baseline": {"value": value, "unit": "particle-scans/s", "cores": procs, "kind": "port",
+                         "sample": "%d processes x 1 particle x %d steps per bench step" % (procs, per)},
+        "e2e": {"value": value, "unit": "particle-scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c5"])
+    ap.add_argument("--particles", type=int, default=0, help="particles per GPU (default: the workload's)")
+    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

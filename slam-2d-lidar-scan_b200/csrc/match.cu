@@ -41,10 +41,10 @@ struct StageDev {
   int progLen;               // postfix combine program: >= 0 push leaf, -1 add
   const short* prog;
   // ---- plan
-  int Wmax, Wmap, words, Ppitch, VbPitch, R, TB, Kpad, E;
+  int Wmax, Wmap, words, WT, Ppitch, TB, Kpad, E;
   int bitsInSmem, PInSmem, scoresInSmem, needScores;
-  int oBits, oVb, oNb, oAct, oRow, oCol, oP, oLists, oCnt, oScores, oDx, oDy, oLeaf;
-  size_t gBits, gP, gScores;  // byte offsets inside a CTA's global scratch slot
+  int oBits, oBitsT, oDil, oVw, oRow, oCol, oP, oLists, oCnt, oScores, oDx, oDy, oLeaf;
+  size_t gBits, gBitsT, gDil, gP, gScores;  // byte offsets inside a CTA's global scratch slot
 };
 
 struct MatchParams {
@@ -68,15 +68,120 @@ struct MatchParams {
 // ------------------------------------------------------------------------------------------------ device
 __device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -1 - i : (i >= n ? 2 * n - 1 - i : i); }
 
-struct Fetch {
+constexpr int GRP = 2;   // adjacent x offsets handled by one thread (share the key / bitmap lookups)
+
+// Dense field (coarse stage, shared memory): GRP consecutive cells of one row per point.
+struct FetchDense {
   const unsigned* list;  // sorted unique keys (x << 16 | y)
-  const double* base;    // field pointer pre-offset by (dy, dx)
+  const double* base;    // field pointer pre-offset by (dy, dx0)
   int pitch;
-  __device__ __forceinline__ double operator()(int k) const {
-    unsigned key = list[k];
-    return base[(int)(key & 0xffffu) * pitch + (int)(key >> 16)];
+  __device__ __forceinline__ void get(int k, double (&v)[GRP]) const {
+    const unsigned key = list[k];
+    const double* q = base + (int)(key & 0xffffu) * pitch + (int)(key >> 16);
+#pragma unroll
+    for (int g = 0; g < GRP; ++g) v[g] = q[g];
   }
 };
+
+// Sparse field: materialised only where the activity bitmap is set; everywhere else it equals the
+// all-background constant B2 (produced on the host by the same operation order as the blur).
+struct FetchGated {
+  const unsigned* list;
+  const double* P;       // field base (no offset applied)
+  const unsigned* dil;   // activity bitmap [rows][words]
+  double B2;
+  int pitch, words, dy, dx;
+  __device__ __forceinline__ void get(int k, double (&v)[GRP]) const {
+    const unsigned key = list[k];
+    const int xx = (int)(key >> 16) + dx, yy = (int)(key & 0xffffu) + dy;
+    const int wi = xx >> 5;
+    const unsigned* row = dil + yy * words;
+    const unsigned w0 = row[wi];
+    const unsigned w1 = (wi + 1 < words) ? row[wi + 1] : 0u;
+    const unsigned f = __funnelshift_r(w0, w1, xx & 31);
+#pragma unroll
+    for (int g = 0; g < GRP; ++g) v[g] = B2;
+    if (f & ((1u << GRP) - 1u)) {
+      const double* q = P + yy * pitch + xx;
+#pragma unroll
+      for (int g = 0; g < GRP; ++g)
+        if ((f >> g) & 1u) v[g] = q[g];
+    }
+  }
+};
+
+// numpy pairwise_sum for GRP independent sums sharing the index stream: n <= 128 branch inline, recursion
+// (split at n/2 rounded down to a multiple of 8, depth <= 3 for n <= 512) as nested loops around ONE leaf body.
+template <class F>
+__device__ __forceinline__ void leaf_sum_g(const F& f, int off, int n, double (&out)[GRP]) {
+  if (n < 8) {
+#pragma unroll
+    for (int g = 0; g < GRP; ++g) out[g] = 0.0;
+    for (int i = 0; i < n; ++i) {
+      double v[GRP];
+      f.get(off + i, v);
+#pragma unroll
+      for (int g = 0; g < GRP; ++g) out[g] = dadd(out[g], v[g]);
+    }
+    return;
+  }
+  double r[8][GRP];
+#pragma unroll
+  for (int l = 0; l < 8; ++l) f.get(off + l, r[l]);
+  const int m = n - (n & 7);
+  for (int i = 8; i < m; i += 8) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      double v[GRP];
+      f.get(off + i + l, v);
+#pragma unroll
+      for (int g = 0; g < GRP; ++g) r[l][g] = dadd(r[l][g], v[g]);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < GRP; ++g)
+    out[g] = dadd(dadd(dadd(r[0][g], r[1][g]), dadd(r[2][g], r[3][g])), dadd(dadd(r[4][g], r[5][g]), dadd(r[6][g], r[7][g])));
+  for (int i = m; i < n; ++i) {
+    double v[GRP];
+    f.get(off + i, v);
+#pragma unroll
+    for (int g = 0; g < GRP; ++g) out[g] = dadd(out[g], v[g]);
+  }
+}
+
+__device__ __forceinline__ int pw_split(int n) {   // numpy: n2 = n / 2; n2 -= n2 % 8
+  int n2 = n / 2;
+  return n2 - (n2 % 8);
+}
+
+template <class F>
+__device__ __forceinline__ void pairwise_g(const F& f, int n, double (&out)[GRP]) {
+  const int c1 = n > 128 ? 2 : 1;
+  for (int i1 = 0; i1 < c1; ++i1) {
+    const int s1 = c1 == 2 ? pw_split(n) : n;
+    const int o1 = i1 ? s1 : 0, n1 = c1 == 2 ? (i1 ? n - s1 : s1) : n;
+    const int c2 = n1 > 128 ? 2 : 1;
+    double acc2[GRP];
+    for (int i2 = 0; i2 < c2; ++i2) {
+      const int s2 = c2 == 2 ? pw_split(n1) : n1;
+      const int o2 = o1 + (i2 ? s2 : 0), n2 = c2 == 2 ? (i2 ? n1 - s2 : s2) : n1;
+      const int c3 = n2 > 128 ? 2 : 1;
+      double acc3[GRP];
+      for (int i3 = 0; i3 < c3; ++i3) {
+        const int s3 = c3 == 2 ? pw_split(n2) : n2;
+        const int o3 = o2 + (i3 ? s3 : 0), n3 = c3 == 2 ? (i3 ? n2 - s3 : s3) : n2;
+        double leaf[GRP];
+        leaf_sum_g(f, o3, n3, leaf);          // n3 <= 128 for n <= 512
+#pragma unroll
+        for (int g = 0; g < GRP; ++g) acc3[g] = i3 ? dadd(acc3[g], leaf[g]) : leaf[g];
+      }
+#pragma unroll
+      for (int g = 0; g < GRP; ++g) acc2[g] = i2 ? dadd(acc2[g], acc3[g]) : acc3[g];
+    }
+#pragma unroll
+    for (int g = 0; g < GRP; ++g) out[g] = i1 ? dadd(out[g], acc2[g]) : acc2[g];
+  }
+}
 
 // numpy pairwise_sum, n <= 128 branch (8 running lanes, fixed tree, sequential tail)
 template <class F>
@@ -252,22 +357,24 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
   const int nStrips = (Wx + 31) >> 5;
 
   unsigned* bits = S.bitsInSmem ? (unsigned*)(smem + S.oBits) : (unsigned*)(gslot + S.gBits);
-  double* Vb = (double*)(smem + S.oVb);
-  unsigned* nb = (unsigned*)(smem + S.oNb);          // [R][words + 2]
-  unsigned* act = (unsigned*)(smem + S.oAct);        // [Wmax][actWords]
+  unsigned* bitsT = S.bitsInSmem ? (unsigned*)(smem + S.oBitsT) : (unsigned*)(gslot + S.gBitsT);  // [col][WT] transposed
+  unsigned* dil = S.bitsInSmem ? (unsigned*)(smem + S.oDil) : (unsigned*)(gslot + S.gDil);   // activity bitmap
+  const int WT = S.WT;
+  double* Vw = (double*)(smem + S.oVw) + warp * 64;  // per-warp scratch: first-pass values of a tile + halo
   short* rowMap = (short*)(smem + S.oRow);
   short* colMap = (short*)(smem + S.oCol);
   double* Pf = S.PInSmem ? (double*)(smem + S.oP) : (double*)(gslot + S.gP);
   const int Pp = S.Ppitch;
-  const int actWords = (words + 31) >> 5;
+  const bool dense = S.PInSmem != 0;                 // coarse: dense field in shared memory, ungated gathers
 
   __syncthreads();  // previous users of the arena are done
   if (cyc && tid == 0) cyc[0] -= clock64();
 
   // ---- B. clear bitmap, float64 index maps (:36 via :173-176) -- rows of OccupancyGridX are identical
   for (int i = tid; i < Wy * words; i += NT) bits[i] = 0u;
-  for (int i = tid; i < Wy * actWords; i += NT) act[i] = 0u;
-  for (int i = tid; i < S.R * (words + 2); i += NT) nb[i] = 0u;
+  for (int i = tid; i < Wx * WT; i += NT) bitsT[i] = 0u;
+  if (dense)
+    for (int i = tid; i < Wy * Pp; i += NT) Pf[i] = S.B2;
   for (int j = tid; j < ncols; j += NT) {
     int c = (int)ddiv(dsub(P.gridX[mx0 + j], xr0), ul);
     if (c < 0 || c >= Wx) { status |= SLAM_ST_INDEX_OUT_OF_FIELD; c = min(max(c, 0), Wx - 1); }
@@ -287,7 +394,10 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
     const int npairs = (mx1 - mxa + 1) >> 1;
     for (int i = warp; i < nrows; i += NW) {
       const float4* rowp = (const float4*)(g + ((size_t)(my0 + i) * P.pitch + mxa) * 2);
-      const int rbase = (int)rowMap[i] * words;
+      const int fr = (int)rowMap[i];
+      const int rbase = fr * words;
+      const int tw = fr >> 5;
+      const unsigned tb = 1u << (fr & 31);
       for (int q0 = 0; q0 < npairs; q0 += 8 * 32) {
         float4 v[8];
 #pragma unroll
@@ -302,10 +412,12 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
           if (2.f * v[u].x > v[u].y && j0 >= 0 && j0 < ncols) {
             int c = colMap[j0];
             atomicOr(&bits[rbase + (c >> 5)], 1u << (c & 31));
+            atomicOr(&bitsT[c * WT + tw], tb);
           }
           if (2.f * v[u].z > v[u].w && j0 + 1 >= 0 && j0 + 1 < ncols) {
             int c = colMap[j0 + 1];
             atomicOr(&bits[rbase + (c >> 5)], 1u << (c & 31));
+            atomicOr(&bitsT[c * WT + tw], tb);
           }
         }
       }
@@ -314,79 +426,125 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
   __syncthreads();
   if (cyc && tid == 0) { long long t = clock64(); cyc[0] += t; cyc[1] -= t; }
 
-  // ---- D. separable blur in scipy's order, chunk of R rows at a time
-  double mn = 0.0;   // every field value is <= 0
-  for (int i0 = 0; i0 < Wy; i0 += S.R) {
-    const int rows = min(S.R, Wy - i0);
-    // first pass (axis 0): depends only on the 2r+1 occupancy bits of the column
-    for (int s = warp; s < nStrips; s += NW) {
-      unsigned sr = 0;
-      for (int d = -r; d <= r; ++d) {
-        unsigned wv = bits[reflect_idx(i0 + d, Wy) * words + s];
-        sr |= ((wv >> lane) & 1u) << (d + r);
-      }
-      const int j = 32 * s + lane;
-      for (int ii = 0; ii < rows; ++ii) {
-        if (ii > 0) {
-          unsigned wv = bits[reflect_idx(i0 + ii + r, Wy) * words + s];
-          sr = (sr >> 1) | (((wv >> lane) & 1u) << (2 * r));
+  // ---- D. separable blur in scipy's order, only where the result can differ from the background.
+  // D1. activity bitmap: cell (i, j) is active iff an occupied cell lies within +-r rows and +-r columns
+  //     (reflected taps always fall inside that span, so plain dilation is exact).
+  {
+    const int seg = words <= 16 ? 16 : 32;               // lanes per row
+    if (words <= 32) {
+      const int rowsPerWarp = 32 / seg;
+      const int sub = lane / seg, w = lane - sub * seg;
+      for (int i0 = warp * rowsPerWarp; i0 < Wy; i0 += NW * rowsPerWarp) {
+        const int i = i0 + sub;
+        unsigned v = 0u;
+        if (i < Wy && w < words)
+          for (int d = -r; d <= r; ++d) v |= bits[reflect_idx(i + d, Wy) * words + w];
+        unsigned lo = __shfl_up_sync(FULL, v, 1, seg), hi = __shfl_down_sync(FULL, v, 1, seg);
+        if (w == 0) lo = 0u;
+        if (w >= words - 1) hi = 0u;
+        unsigned dl = v;
+        for (int k = 1; k <= r; ++k) dl |= (v << k) | (v >> k) | (lo >> (32 - k)) | (hi << (32 - k));
+        if (i < Wy && w < words) {
+          const int valid = Wx - 32 * w;                 // columns of this word that exist
+          if (valid < 32) dl &= valid <= 0 ? 0u : ((1u << valid) - 1u);
+          dil[i * words + w] = dl;
         }
-        unsigned nbm = __ballot_sync(FULL, sr != 0u);
-        double v = S.B1;
-        if (nbm != 0u) {
-          v = ((sr >> r) & 1u) ? 0.0 : S.C0;
-          for (int jj = 0; jj < r; ++jj) {
-            int occ = (int)((sr >> jj) & 1u) + (int)((sr >> (2 * r - jj)) & 1u);
-            double t = occ == 0 ? S.T2[jj] : (occ == 1 ? S.T1[jj] : 0.0);
-            v = dadd(v, t);
+      }
+    } else {
+      for (int t = tid; t < Wy * words; t += NT) {
+        const int i = t / words, w = t - i * words;
+        unsigned lo = 0u, v = 0u, hi = 0u;
+        for (int d = -r; d <= r; ++d) {
+          const unsigned* row = bits + reflect_idx(i + d, Wy) * words;
+          v |= row[w];
+          if (w > 0) lo |= row[w - 1];
+          if (w + 1 < words) hi |= row[w + 1];
+        }
+        unsigned dl = v;
+        for (int k = 1; k <= r; ++k) dl |= (v << k) | (v >> k) | (lo >> (32 - k)) | (hi << (32 - k));
+        const int valid = Wx - 32 * w;
+        if (valid < 32) dl &= valid <= 0 ? 0u : ((1u << valid) - 1u);
+        dil[t] = dl;
+      }
+    }
+  }
+  __syncthreads();
+  // D2. blur the active tiles (32 columns x 1 row).  First pass (axis 0) depends only on the 2r+1 occupancy bits
+  //     of a column: out = x[c]*w[r]; out += (x[c+j] + x[c-j])*w[j+r], j = -r..-1, with x in {log(missProb), 0}.
+  double mn = 0.0;                 // every field value is <= 0
+  int nActive = 0;                 // active cells seen by this thread's warp (lane 0 keeps the count)
+  const int nTiles = Wy * words;
+  for (int tb = warp * 32; tb < nTiles; tb += NW * 32) {
+    const int tmine = tb + lane;
+    const unsigned wmine = tmine < nTiles ? dil[tmine] : 0u;
+    unsigned am = __ballot_sync(FULL, wmine != 0u);
+    while (am) {
+      const int b = __ffs(am) - 1;
+      am &= am - 1;
+      const unsigned dl = __shfl_sync(FULL, wmine, b);
+      const int t = tb + b;
+      const int i = t / words, w = t - i * words;
+      // virtual columns 32w-r .. 32w+31+r; lane handles vc0 = 32w-r+lane and (lane < 2r) vc1 = vc0+32
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && lane >= 2 * r) break;
+        const int col = reflect_idx(32 * w - r + lane + 32 * h, Wx);
+        const unsigned* colBits = bitsT + col * WT;
+        unsigned sr;
+        if (i - r >= 0 && i + r < Wy) {         // the column's 2r+1 rows straight out of the transposed bitmap
+          const int lo = i - r;
+          sr = __funnelshift_r(colBits[lo >> 5], colBits[(lo >> 5) + 1], lo & 31) & ((2u << (2 * r)) - 1u);
+        } else {                                // top / bottom border: reflected rows, bit by bit
+          sr = 0u;
+          for (int d = -r; d <= r; ++d) {
+            const int rr = reflect_idx(i + d, Wy);
+            sr |= ((colBits[rr >> 5] >> (rr & 31)) & 1u) << (d + r);
           }
         }
-        if (j < Wx) Vb[ii * S.VbPitch + r + j] = v;
-        if (lane == 0) nb[ii * (words + 2) + s + 1] = nbm;
-      }
-    }
-    __syncthreads();
-    // reflect halo of the row buffer
-    for (int t = tid; t < rows * 2 * r; t += NT) {
-      int ii = t / (2 * r), k = t % (2 * r);
-      double* row = Vb + ii * S.VbPitch + r;
-      if (k < r) row[-1 - k] = row[k];
-      else { int kk = k - r; row[Wx + kk] = row[Wx - 1 - kk]; }
-    }
-    __syncthreads();
-    // second pass (axis 1)
-    for (int t = warp; t < rows * nStrips; t += NW) {
-      const int ii = t / nStrips, s = t - ii * nStrips;
-      const unsigned* nbr = nb + ii * (words + 2) + s;
-      const unsigned lo = nbr[0], m = nbr[1], hi = (s + 1 < nStrips) ? nbr[2] : 0u;
-      unsigned dil = m;
-      for (int k = 1; k <= r; ++k) dil |= (m << k) | (m >> k) | (lo >> (32 - k)) | (hi << (32 - k));
-      const int j = 32 * s + lane;
-      double val = S.B2;
-      if (dil != 0u) {
-        if ((dil >> lane) & 1u) {
-          const double* c = Vb + ii * S.VbPitch + r + j;
-          val = dmul(c[0], S.w[r]);
-          for (int jj = 0; jj < r; ++jj) val = dadd(val, dmul(dadd(c[jj - r], c[r - jj]), S.w[jj]));
+        double v = S.B1;
+        if (sr != 0u) {
+          v = ((sr >> r) & 1u) ? 0.0 : S.C0;
+          for (int jj = 0; jj < r; ++jj) {
+            const int occ = (int)((sr >> jj) & 1u) + (int)((sr >> (2 * r - jj)) & 1u);
+            const double tt = occ == 0 ? S.T2[jj] : (occ == 1 ? S.T1[jj] : 0.0);
+            v = dadd(v, tt);
+          }
         }
-        if (lane == 0) atomicOr(&act[(i0 + ii) * actWords + (s >> 5)], 1u << (s & 31));
+        Vw[lane + 32 * h] = v;
       }
-      if (j < Wx) {
-        Pf[(size_t)(i0 + ii) * Pp + j] = val;
+      __syncwarp();
+      // second pass (axis 1) for the active cells of the tile
+      if ((dl >> lane) & 1u) {
+        const double* c = Vw + lane + r;          // virtual column of cell 32w+lane
+        double val = dmul(c[0], S.w[r]);
+        for (int jj = 0; jj < r; ++jj) val = dadd(val, dmul(dadd(c[jj - r], c[r - jj]), S.w[jj]));
+        Pf[(size_t)i * Pp + 32 * w + lane] = val;
         mn = fmin(mn, val);
       }
+      if (lane == 0) nActive += __popc(dl);
+      __syncwarp();
     }
-    __syncthreads();
   }
-  // ---- E. probMin, clamp (:43-44); only tiles that are not pure background can exceed the threshold
+  // ---- E. probMin, clamp (:43-44).  Inactive cells hold exactly B2 (the minimum of the value set).
+  if (lane == 0) bs.ival[warp] = nActive;
+  __syncthreads();
+  int activeCells = 0;
+  for (int w2 = 0; w2 < NW; ++w2) activeCells += bs.ival[w2];
+  if (activeCells < Wx * Wy) mn = fmin(mn, S.B2);
   const double probMin = block_min(mn, bs);
   const double thr = dmul(0.5, probMin);
-  for (int t = warp; t < Wy * nStrips; t += NW) {
-    const int i = t / nStrips, s = t - i * nStrips;
-    if ((act[i * actWords + (s >> 5)] >> (s & 31)) & 1u) {
-      const int j = 32 * s + lane;
-      if (j < Wx) {
-        double* q = Pf + (size_t)i * Pp + j;
+  for (int tb = warp * 32; tb < nTiles; tb += NW * 32) {
+    const int tmine = tb + lane;
+    const unsigned wmine = tmine < nTiles ? dil[tmine] : 0u;
+    unsigned am = __ballot_sync(FULL, wmine != 0u);
+    while (am) {
+      const int b = __ffs(am) - 1;
+      am &= am - 1;
+      const unsigned dl = __shfl_sync(FULL, wmine, b);
+      const int t = tb + b;
+      const int i = t / words, w = t - i * words;
+      if ((dl >> lane) & 1u) {
+        double* q = Pf + (size_t)i * Pp + 32 * w + lane;
         if (*q > thr) *q = 0.0;
       }
     }
@@ -395,7 +553,11 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
   if (cyc && tid == 0) { long long t = clock64(); cyc[1] += t; cyc[2] -= t; }
   if (P.dbgProb[stageId]) {
     double* d = P.dbgProb[stageId] + (size_t)p * S.Wmax * S.Wmax;
-    for (int i = tid; i < Wy * Wx; i += NT) d[(i / Wx) * S.Wmax + (i % Wx)] = Pf[(size_t)(i / Wx) * Pp + (i % Wx)];
+    for (int i = tid; i < Wy * Wx; i += NT) {
+      const int yy = i / Wx, xx = i - yy * Wx;
+      const bool on = dense || ((dil[yy * words + (xx >> 5)] >> (xx & 31)) & 1u);
+      d[yy * S.Wmax + xx] = on ? Pf[(size_t)yy * Pp + xx] : S.B2;
+    }
     if (tid == 0) { P.dbgDims[stageId][2 * p] = Wy; P.dbgDims[stageId][2 * p + 1] = Wx; }
   }
 
@@ -439,6 +601,7 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
   }
   __syncthreads();
 
+  if (cyc && tid == 0) cyc[2] += clock64();
   // ---- G. per-theta lists + score volume, TB thetas at a time
   unsigned* lists = (unsigned*)(smem + S.oLists);
   int* cnts = (int*)(smem + S.oCnt);
@@ -462,22 +625,40 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
     }
     __syncthreads();
     if (cyc && tid == 0) { long long t = clock64(); cyc[3] += t; cyc[4] -= t; }
-    const int nq = nt * nOff2;
+    const int nGrp = (nOff + GRP - 1) / GRP;
+    const int nq = nt * nOff * nGrp;
     for (int q = tid; q < nq; q += NT) {
-      const int tl = q / nOff2, rem = q - tl * nOff2;
-      const int a = rem / nOff, b = rem - a * nOff;
-      Fetch f;
-      f.list = lists + tl * S.Kpad;
-      f.base = Pf + (a - S.nHalf) * Pp + (b - S.nHalf);
-      f.pitch = Pp;
-      double sc = pairwise<3>(f, 0, cnts[tl]);                     // np.sum(axis=2) :130
-      if (rv) sc = dadd(sc, rv[rem]);                              // + rv + thetaWeight :131
-      if (tw) sc = dadd(sc, tw[rem]);
-      const int flat = (t0 + tl) * nOff2 + rem;
-      if (scores) scores[flat] = sc;
-      if (dvol) dvol[flat] = sc;
-      if (sc != sc) sawNan = true;
-      if (bestIdx < 0 || sc > best) { best = sc; bestIdx = flat; }  // flat increases per thread -> first max kept
+      const int tl = q / (nOff * nGrp), rem0 = q - tl * (nOff * nGrp);
+      const int a = rem0 / nGrp, b0 = (rem0 - a * nGrp) * GRP;
+      double sc[GRP];
+      if (dense) {
+        FetchDense f;
+        f.list = lists + tl * S.Kpad;
+        f.base = Pf + (a - S.nHalf) * Pp + (b0 - S.nHalf);
+        f.pitch = Pp;
+        pairwise_g(f, cnts[tl], sc);                               // np.sum(axis=2) :130
+      } else {
+        FetchGated f;
+        f.list = lists + tl * S.Kpad;
+        f.P = Pf; f.dil = dil; f.B2 = S.B2; f.pitch = Pp; f.words = words;
+        f.dy = a - S.nHalf; f.dx = b0 - S.nHalf;
+        pairwise_g(f, cnts[tl], sc);
+      }
+#pragma unroll
+      for (int g = 0; g < GRP; ++g) {
+        const int b = b0 + g;
+        if (b < nOff) {
+          const int rem = a * nOff + b;
+          double v = sc[g];
+          if (rv) v = dadd(v, rv[rem]);                            // + rv + thetaWeight :131
+          if (tw) v = dadd(v, tw[rem]);
+          const int flat = (t0 + tl) * nOff2 + rem;
+          if (scores) scores[flat] = v;
+          if (dvol) dvol[flat] = v;
+          if (v != v) sawNan = true;
+          if (bestIdx < 0 || v > best || (v == best && flat < bestIdx)) { best = v; bestIdx = flat; }
+        }
+      }
     }
     __syncthreads();
     if (cyc && tid == 0) cyc[4] += clock64();
@@ -732,63 +913,65 @@ static int plan_stage(slam_matcher* m, const slam_geometry* g, const slam_stage_
   S.Wmax = (int)(2.0 * R / d.unitLength) + 2;
   S.Wmap = (int)(2.0 * R / g->unit) + 3;
   if (S.Wmax > 32000 || S.Wmap > 32000) return fail(SLAM_E_UNSUPPORTED, "search window too large");
-  S.words = (S.Wmax + 31) / 32;
+  S.words = (S.Wmax + GRP + 31) / 32;
+  S.WT = (S.Wmax + 31) / 32 + 1;
+  if (S.WT % 2 == 0) S.WT += 1;          // odd column pitch: conflict-free transposed-bitmap reads
   S.Kpad = (g->K + 3) & ~3;
   S.E = g->K <= 256 ? 8 : 16;
   S.needScores = (stageId == 0);
-  const int actWords = (S.words + 31) / 32;
   const size_t bitsBytes = (size_t)S.Wmax * S.words * 4;
-  const size_t actBytes = (size_t)S.Wmax * actWords * 4;
+  const size_t bitsTBytes = (size_t)S.Wmax * S.WT * 4;
   const size_t mapBytes = align_up((size_t)S.Wmap * 2, 16);
   const size_t scoreBytes = S.needScores ? (size_t)S.nPoses * 8 : 0;
   const size_t leafBytes = S.needScores ? (size_t)S.nLeaves * 8 : 0;
   const size_t dxyBytes = align_up((size_t)g->K * 8, 16);
   // field pitch: conflict-free shared-memory gathers want pitch == nOff (mod 16) doubles
   int pp = S.Wmax;
-  while ((pp % 16) != (S.nOff % 16)) ++pp;
+  if (stageId == 0)
+    while ((pp % 16) != (S.nOff % 16)) ++pp;
+  else
+    pp = (pp + 3) & ~3;
   S.Ppitch = pp;
-  const size_t PBytes = (size_t)S.Wmax * S.Ppitch * 8;
-  S.VbPitch = S.Wmax + 2 * r;
+  const size_t PBytes = (size_t)(S.Wmax + 1) * S.Ppitch * 8;   // one slack row: grouped gathers may overshoot
   // try placements from fastest to most frugal
   for (int attempt = 0; attempt < 8; ++attempt) {
-    S.PInSmem = (attempt & 4) ? 0 : (stageId == 0);     // fine field always in the global slot
+    S.PInSmem = (attempt & 4) ? 0 : (stageId == 0);     // fine field: sparse, in the global slot (L2)
     S.scoresInSmem = (attempt & 2) ? 0 : 1;
     S.bitsInSmem = (attempt & 1) ? 0 : 1;
-    for (int Rr : {16, 8, 4, 2}) {
-      for (int TB : {S.nTheta, (S.nTheta + 1) / 2, NW, 8, 4}) {
-        if (TB > S.nTheta || TB < 1) continue;
-        S.R = Rr;
-        S.TB = TB;
-        size_t off = 0;
-        auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return (int)o; };
-        S.oP = S.PInSmem ? take(PBytes) : 0;
-        S.oAct = take(actBytes);
-        S.oDx = take(dxyBytes);
-        S.oDy = take(dxyBytes);
-        const size_t common = off;
-        // blur-phase buffers
-        S.oBits = S.bitsInSmem ? take(bitsBytes) : 0;
-        S.oVb = take((size_t)Rr * S.VbPitch * 8);
-        S.oNb = take((size_t)Rr * (S.words + 2) * 4);
-        S.oRow = take(mapBytes);
-        S.oCol = take(mapBytes);
-        const size_t blurEnd = off;
-        // correlate-phase buffers alias the blur-phase ones
-        off = common;
-        S.oLists = take((size_t)TB * S.Kpad * 4);
-        S.oCnt = take((size_t)TB * 4);
-        S.oScores = (S.needScores && S.scoresInSmem) ? take(scoreBytes) : 0;
-        S.oLeaf = take(leafBytes);
-        const size_t need = std::max(blurEnd, off);
-        if (need <= smemBudget) {
-          smemNeed = std::max(smemNeed, need);
-          size_t g0 = slotBytes;
-          S.gBits = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsBytes, 256);
-          S.gP = g0; g0 += S.PInSmem ? 0 : align_up(PBytes, 256);
-          S.gScores = g0; g0 += (S.needScores && !S.scoresInSmem) ? align_up(scoreBytes, 256) : 0;
-          slotBytes = g0;
-          return 0;
-        }
+    for (int TB : {S.nTheta, (S.nTheta + 1) / 2, NW, 8, 4}) {
+      if (TB > S.nTheta || TB < 1) continue;
+      S.TB = TB;
+      size_t off = 0;
+      auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return (int)o; };
+      S.oP = S.PInSmem ? take(PBytes) : 0;
+      S.oDil = S.bitsInSmem ? take(bitsBytes) : 0;      // activity bitmap lives through the correlation
+      S.oDx = take(dxyBytes);
+      S.oDy = take(dxyBytes);
+      S.oVw = take((size_t)NW * 64 * 8);
+      const size_t common = off;
+      // window / blur-phase buffers
+      S.oBits = S.bitsInSmem ? take(bitsBytes) : 0;
+      S.oBitsT = S.bitsInSmem ? take(bitsTBytes) : 0;
+      S.oRow = take(mapBytes);
+      S.oCol = take(mapBytes);
+      const size_t blurEnd = off;
+      // correlate-phase buffers alias the blur-phase ones
+      off = common;
+      S.oLists = take((size_t)TB * S.Kpad * 4);
+      S.oCnt = take((size_t)TB * 4);
+      S.oScores = (S.needScores && S.scoresInSmem) ? take(scoreBytes) : 0;
+      S.oLeaf = take(leafBytes);
+      const size_t need = std::max(blurEnd, off);
+      if (need <= smemBudget) {
+        smemNeed = std::max(smemNeed, need);
+        size_t g0 = slotBytes;
+        S.gBits = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsBytes, 256);
+        S.gBitsT = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsTBytes, 256);
+        S.gDil = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsBytes, 256);
+        S.gP = g0; g0 += S.PInSmem ? 0 : align_up(PBytes, 256);
+        S.gScores = g0; g0 += (S.needScores && !S.scoresInSmem) ? align_up(scoreBytes, 256) : 0;
+        slotBytes = g0;
+        return 0;
       }
     }
   }
@@ -847,7 +1030,7 @@ extern "C" void slam_matcher_set_debug(slam_matcher* m, long long* d_cycles, int
 extern "C" int slam_matcher_num_ctas(const slam_matcher* m) { return m->numCtas; }
 extern "C" int slam_matcher_plan(const slam_matcher* m, int stage, int* out8) {
   const StageDev& S = m->P.st[stage & 1];
-  out8[0] = S.PInSmem; out8[1] = S.scoresInSmem; out8[2] = S.bitsInSmem; out8[3] = S.R;
+  out8[0] = S.PInSmem; out8[1] = S.scoresInSmem; out8[2] = S.bitsInSmem; out8[3] = S.words;
   out8[4] = S.TB; out8[5] = S.Ppitch; out8[6] = (int)m->smemBytes; out8[7] = (int)(m->P.slotBytes >> 10);
   return 0;
 }

@@ -98,8 +98,11 @@ class MatcherEngine:
 
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
-        if h and nat is not None:
-            nat.lib.slam_matcher_destroy(h)
+        try:
+            if h:
+                nat.lib.slam_matcher_destroy(h)
+        except Exception:       # interpreter shutdown: the module globals may already be gone
+            pass
 
     # -- priors of the coarse stage (:95-110), host side, reference expressions
     def offset_axis(self, stage=0):

@@ -109,6 +109,11 @@ class ParticleFilter:
         self._cdf = torch.zeros(n, **f64)
         self._ridx = torch.zeros(n, **i32)
         self._traj = []
+        self.keepTrajectory = True           # per-step [N][2] device copy of the matched positions
+        self.kernelLaunches = 0              # kernels of this library enqueued so far
+        self.matchEvents = None              # list -> (start, end) CUDA events around every match launch
+        self.h2dBytes = 0
+        self.d2hBytes = 0
         self._prevRaw = [None] * n
         self._prevRawHeading = [None] * n
         self._rawUniform = True
@@ -138,6 +143,7 @@ class ParticleFilter:
         """Normalise, then the reference's variance trigger (FastSlam.py:30-41).  Synchronises (returns a bool)."""
         self._normalize()
         out = torch.cat([self._out[:2], self.status.max().to(torch.float64).view(1)]).cpu()
+        self.d2hBytes += 24
         raise_for_status(int(out[2].item()))
         self.lastVariance = float(out[0].item())
         return bool(out[1].item() != 0.0)
@@ -170,77 +176,101 @@ class ParticleFilter:
     def _normalize(self):
         nat.check(nat.lib.slam_normalize_weights(self.numParticles, self.weights.data_ptr(), self._out.data_ptr(),
                                                  _stream(self.geom.device)))
+        self.kernelLaunches += 1
 
-    def _update(self, lo, hi, reading, count):
-        """Particle.update (FastSlam.py:122-135) for particles [lo, hi)."""
-        n, dev, K = hi - lo, self.geom.device, self.geom.numSamplesPerRev
+    def _prepare(self, reading, count, n, prevRaw, prevRawHeading, out=None, uniforms=None):
+        """Host part of Particle.update: the raw-odometry scalars (identical for every particle), the RNG draws
+        and the radial prior.  Fills a pinned staging row [ranges | uniforms | rv] and returns the launch record."""
+        K, N, n2 = self.geom.numSamplesPerRev, self.numParticles, self.engine.nOffC ** 2
+        h = self._stage_h if out is None else out
+        h[:K] = torch.from_numpy(np.asarray(reading['range'], dtype=np.float64))
+        rec = dict(count=count, reading=reading, mode=0, rawTurn=0.0, newRawHeading=None)
+        if count == 1:
+            return rec
+        raw = reading
+        dx, dy = raw['x'] - prevRaw['x'], raw['y'] - prevRaw['y']
+        estMovingDist = math.sqrt(dx ** 2 + dy ** 2)                                              # :82
+        rawMove = math.sqrt((raw['x'] - prevRaw['x']) ** 2 + (raw['y'] - prevRaw['y']) ** 2)    # :86
+        if rawMove > 0.3:                                                                         # :88-101
+            rec["newRawHeading"] = math.acos(dx / rawMove) if dy > 0 else -math.acos(dx / rawMove)
+            if prevRawHeading is not None:
+                rec["mode"], rec["rawTurn"] = 1, rec["newRawHeading"] - prevRawHeading
+        rec["rawTheta"], rec["prevRawTheta"] = raw['theta'], prevRaw['theta']
+        if uniforms is None:
+            uniforms = np.random.random_sample(n)                           # one draw per matchScan, particle order
+        h[K:K + n] = torch.from_numpy(np.ascontiguousarray(uniforms, dtype=np.float64))
+        h[K + N:K + N + n2] = torch.from_numpy(self.engine.radial_prior(estMovingDist).reshape(-1))
+        return rec
+
+    def _launch(self, lo, hi, rec, d_stage):
+        """Device part of Particle.update for particles [lo, hi): kernel launches only, no host synchronisation."""
+        n, dev, K, N = hi - lo, self.geom.device, self.geom.numSamplesPerRev, self.numParticles
         st = _stream(dev)
         eng = self.engine
         n2 = eng.nOffC ** 2
-        N = self.numParticles
-        h = self._stage_h
-        if self._stage_busy:
-            self._stage_ev.synchronize()         # previous async H2D out of the pinned staging buffer has landed
-            self._stage_busy = False
-        h[:K] = torch.from_numpy(np.asarray(reading['range'], dtype=np.float64))
         matched = self._matched[lo:hi]
         status = self.status[lo:hi]
+        count, reading = rec["count"], rec["reading"]
         if count == 1:
             # matchedReading, confidence = reading, 1 (:123-125)
-            self._stage_d[:K].copy_(h[:K], non_blocking=True)
-            self._stage_ev.record(torch.cuda.current_stream(dev))
-            self._stage_busy = True
             matched.copy_(torch.tensor([reading['x'], reading['y'], reading['theta']], dtype=torch.float64))
             self.hasHeading[lo:hi] = 0
             self.prevMatched[lo:hi] = matched
-            newRawHeading = None
         else:
-            raw, prevRaw, prevRawHeading = reading, self._prevRaw[lo], self._prevRawHeading[lo]
-            dx, dy = raw['x'] - prevRaw['x'], raw['y'] - prevRaw['y']
-            estMovingDist = math.sqrt(dx ** 2 + dy ** 2)                                     # :82
-            rawMove = math.sqrt((raw['x'] - prevRaw['x']) ** 2 + (raw['y'] - prevRaw['y']) ** 2)   # :86
-            mode, rawTurn, newRawHeading = 0, 0.0, None
-            if rawMove > 0.3:                                                                # :88-101
-                newRawHeading = math.acos(dx / rawMove) if dy > 0 else -math.acos(dx / rawMove)
-                if prevRawHeading is not None:
-                    mode, rawTurn = 1, newRawHeading - prevRawHeading
-            h[K:K + n] = torch.from_numpy(np.random.random_sample(n))       # one draw per matchScan, particle order
-            h[K + N:K + N + n2] = torch.from_numpy(eng.radial_prior(estMovingDist).reshape(-1))
-            self._stage_d.copy_(h, non_blocking=True)
-            self._stage_ev.record(torch.cuda.current_stream(dev))
-            self._stage_busy = True
-            d_u = self._stage_d[K:K + n]
-            d_rv = self._stage_d[K + N:K + N + n2]
+            d_u = d_stage[K:K + n]
+            d_rv = d_stage[K + N:K + N + n2]
             nat.check(nat.lib.slam_propose_poses(
-                n, self.prevMatched[lo:hi].data_ptr(), raw['theta'], prevRaw['theta'], mode, rawTurn,
-                self.prevHeading[lo:hi].data_ptr(), self.hasHeading[lo:hi].data_ptr(), self._est[lo:hi].data_ptr(),
-                self._phi[lo:hi].data_ptr(), self._hasPhi[lo:hi].data_ptr(), status.data_ptr(), st))
+                n, self.prevMatched[lo:hi].data_ptr(), rec["rawTheta"], rec["prevRawTheta"], rec["mode"],
+                rec["rawTurn"], self.prevHeading[lo:hi].data_ptr(), self.hasHeading[lo:hi].data_ptr(),
+                self._est[lo:hi].data_ptr(), self._phi[lo:hi].data_ptr(), self._hasPhi[lo:hi].data_ptr(),
+                status.data_ptr(), st))
             tw = None
-            if mode == 1:
+            if rec["mode"] == 1:
                 tw = self._tw[lo:hi]
                 nat.check(nat.lib.slam_motion_priors(n, eng.stageInfo[0]["nHalf"], eng.heading_coef,
                                                      self._phi[lo:hi].data_ptr(), self._hasPhi[lo:hi].data_ptr(),
                                                      tw.data_ptr(), st))
-            eng.match(self.grids[lo:hi], n, self._stage_d[:K], self._est[lo:hi], d_rv, tw, d_u, matched,
+            if self.matchEvents is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record(torch.cuda.current_stream(dev))
+            eng.match(self.grids[lo:hi], n, d_stage[:K], self._est[lo:hi], d_rv, tw, d_u, matched,
                       self._conf[lo:hi], self._idx[lo:hi], status)
+            if self.matchEvents is not None:
+                ev1.record(torch.cuda.current_stream(dev))
+                self.matchEvents.append((ev0, ev1))
             nat.check(nat.lib.slam_finish_step(n, matched.data_ptr(), self._conf[lo:hi].data_ptr(),
                                                self.prevMatched[lo:hi].data_ptr(), self.prevHeading[lo:hi].data_ptr(),
                                                self.hasHeading[lo:hi].data_ptr(), self.weights[lo:hi].data_ptr(), st))
-        if n == N:
-            self._traj.append(matched[:, :2].clone())
-        else:
-            if not self._traj or self._traj[-1].shape[0] != N or getattr(self, "_trajCount", None) != count:
-                self._traj.append(torch.zeros((N, 2), dtype=torch.float64, device=dev))
-            self._traj[-1][lo:hi] = matched[:, :2]
-        self._trajCount = count
-        update_grids(self.geom, self.grids[lo:hi], n, self._stage_d[:K], matched, status)    # :133
+        if self.keepTrajectory:
+            if n == N:
+                self._traj.append(matched[:, :2].clone())
+            else:
+                if not self._traj or getattr(self, "_trajCount", None) != count:
+                    self._traj.append(torch.zeros((N, 2), dtype=torch.float64, device=dev))
+                self._traj[-1][lo:hi] = matched[:, :2]
+            self._trajCount = count
+        update_grids(self.geom, self.grids[lo:hi], n, d_stage[:K], matched, status)           # :133
+        self.kernelLaunches += 3 + (0 if count == 1 else 3 + (1 if rec["mode"] == 1 else 0))
+
+    def _update(self, lo, hi, reading, count, uniforms=None):
+        """Particle.update (FastSlam.py:122-135) for particles [lo, hi): host prep, one H2D copy, launches."""
+        n, dev, N = hi - lo, self.geom.device, self.numParticles
+        if self._stage_busy:
+            self._stage_ev.synchronize()         # previous async H2D out of the pinned staging buffer has landed
+            self._stage_busy = False
+        rec = self._prepare(reading, count, n, self._prevRaw[lo], self._prevRawHeading[lo], uniforms=uniforms)
+        self._stage_d.copy_(self._stage_h, non_blocking=True)
+        self._stage_ev.record(torch.cuda.current_stream(dev))
+        self._stage_busy = True
+        self.h2dBytes += self._stage_h.numel() * 8
+        self._launch(lo, hi, rec, self._stage_d)
         if n == N:
             self._prevRaw = [reading] * N
-            self._prevRawHeading = [newRawHeading] * N
+            self._prevRawHeading = [rec["newRawHeading"]] * N
         else:
             for i in range(lo, hi):
                 self._prevRaw[i] = reading
-                self._prevRawHeading[i] = newRawHeading
+                self._prevRawHeading[i] = rec["newRawHeading"]
 
     # ---- conveniences beyond the reference
     def poses(self):

@@ -1,0 +1,55 @@
+"""Per-phase SM-cycle breakdown of the fused match kernel (clock64 at phase boundaries, thread 0 of each CTA).
+Usage (GPU box): python tools/phase_cycles.py [workload] [particles]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+ge.build()
+import slam_2d_lidar_scan_b200 as S  # noqa: E402
+from slam_2d_lidar_scan_b200 import synthetic  # noqa: E402
+
+workload = sys.argv[1] if len(sys.argv) > 1 else "c3"
+spec = synthetic.config(workload)
+n = int(sys.argv[2]) if len(sys.argv) > 2 else spec["N"]
+scene = synthetic.make_scene(seed=0, steps=8, K=spec["K"], fov=spec["og"][4], unit=spec["og"][3])
+np.random.seed(0)
+pf = S.ParticleFilter(n, spec["og"], spec["sm"])
+pf.keepTrajectory = False
+og = S.OccupancyGrid(*pf.geom.args, _geometry=pf.geom)
+for fr in scene["warm"]:
+    og.updateOccupancyGrid(fr)
+pf.grids.copy_(og.device_grid.unsqueeze(0).expand_as(pf.grids))
+nat = S._native
+ctas = nat.lib.slam_matcher_num_ctas(pf.engine.handle)
+cyc = torch.zeros((ctas, 16), dtype=torch.int64, device=pf.geom.device)
+plan = (nat.C.c_int * 8)()
+for s in range(2):
+    nat.lib.slam_matcher_plan(pf.engine.handle, s, nat.C.byref(plan))
+    print("stage", s, "PInSmem,scoresInSmem,bitsInSmem,R,TB,Ppitch,smemBytes,slotKB =", list(plan))
+for count, fr in enumerate(scene["frames"][:6], start=1):
+    if count == 5:
+        nat.lib.slam_matcher_set_debug(pf.engine.handle, cyc.data_ptr(), 0)
+        cyc.zero_()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pf.matchEvents = []
+    pf.updateParticles(fr, count)
+    pf.weightUnbalanced()
+torch.cuda.synchronize()
+ms = [a.elapsed_time(b) for a, b in pf.matchEvents]
+c = cyc.cpu().numpy().astype(np.float64)
+names = ["window", "blur+clamp", "points", "lists(sort)", "correlate", "select", "-", "-"]
+per = c.sum(0) / (2 * n)           # two timed launches
+tot = per.sum()
+print("match kernel ms per launch:", ms)
+for st in range(2):
+    for k in range(6):
+        v = per[8 * st + k]
+        print("%-7s %-12s %10.0f cycles/particle  %5.1f %%" % ("coarse" if st == 0 else "fine", names[k], v, 100 * v / tot))
+print("total %.0f cycles/particle; status max %d" % (tot, int(pf.status.max().item())))
