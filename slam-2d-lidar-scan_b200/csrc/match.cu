@@ -34,6 +34,7 @@ struct StageDev {
   double T1[SLAM_MAX_BLUR_RADIUS], T2[SLAM_MAX_BLUR_RADIUS];  // (c)*w[jj], (c+c)*w[jj]
   double C0;                 // c*w[r]
   double B1, B2;             // all-background value after the first / second pass
+  const double* lutV;        // first-pass value for every (2r+1)-bit column pattern (built once, same op order)
   int nHalf, nOff, nTheta, nPoses;
   const double *thetas, *cosT, *sinT;
   int nLeaves;               // pairwise-sum leaves of the flattened score volume
@@ -41,7 +42,7 @@ struct StageDev {
   int progLen;               // postfix combine program: >= 0 push leaf, -1 add
   const short* prog;
   // ---- plan
-  int Wmax, Wmap, words, WT, Ppitch, TB, Kpad, E;
+  int Wmax, Wmap, words, WT, Ppitch, TB, Kpad, E;   // words includes >= 1 always-zero spare word per row
   int bitsInSmem, PInSmem, scoresInSmem, needScores;
   int oBits, oBitsT, oDil, oVw, oRow, oCol, oP, oLists, oCnt, oScores, oDx, oDy, oLeaf;
   size_t gBits, gBitsT, gDil, gP, gScores;  // byte offsets inside a CTA's global scratch slot
@@ -63,49 +64,89 @@ struct MatchParams {
   double* dbgVol[2];
   long long* dbgCycles;  // [gridDim][16] or null
   int forceExactCdf;
+  int fast;              // plan: 1 = shared-memory plan for both stages, 0 = global-slot plan
 };
 
 // ------------------------------------------------------------------------------------------------ device
 __device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -1 - i : (i >= n ? 2 * n - 1 - i : i); }
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned lds_u32(unsigned a) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+
+// Buffers of the FAST plan are carved out of the dynamic shared-memory array; deriving them from the array itself
+// (instead of a run-time select between shared and global) lets the compiler emit LDS/STS/ATOMS with 32-bit
+// addressing instead of generic loads.  The SLOW plan (windows too large for shared memory) uses the global slot.
+template <class T>
+__device__ __forceinline__ T* sbuf(int off) {
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  return reinterpret_cast<T*>(smem_dyn + off);
+}
+template <bool FAST, class T>
+__device__ __forceinline__ T* buf(int off, unsigned char* gslot, size_t goff) {
+  if (FAST) return sbuf<T>(off);
+  return reinterpret_cast<T*>(gslot + goff);
+}
+
 constexpr int GRP = 2;   // adjacent x offsets handled by one thread (share the key / bitmap lookups)
 
-// Dense field (coarse stage, shared memory): GRP consecutive cells of one row per point.
+// Dense field (coarse stage, shared memory): GRP consecutive cells of one row per point.  32-bit shared addressing.
 struct FetchDense {
-  const unsigned* list;  // sorted unique keys (x << 16 | y)
-  const double* base;    // field pointer pre-offset by (dy, dx0)
+  unsigned listS;        // shared address of the sorted unique keys (x << 16 | y)
+  unsigned baseS;        // shared address of the field
+  unsigned off;          // (dx << 16) + dy, added to the key in one go
   int pitch;
   __device__ __forceinline__ void get(int k, double (&v)[GRP]) const {
-    const unsigned key = list[k];
-    const double* q = base + (int)(key & 0xffffu) * pitch + (int)(key >> 16);
+    const unsigned sxy = lds_u32(listS + 4u * k) + off;
+    const unsigned a = baseS + 8u * ((sxy & 0xffffu) * pitch + (sxy >> 16));
 #pragma unroll
-    for (int g = 0; g < GRP; ++g) v[g] = q[g];
+    for (int g = 0; g < GRP; ++g) v[g] = lds_f64(a + 8u * g);
   }
 };
 
-// Sparse field: materialised only where the activity bitmap is set; everywhere else it equals the
-// all-background constant B2 (produced on the host by the same operation order as the blur).
+// Sparse field: materialised (already clamped) only where the activity bitmap is set; everywhere else it equals the
+// all-background constant B2 (produced on the host by the same operation order as the blur).  Branch-free
+// (predicated loads) so that the eight gathers of one pairwise step are all in flight together.
+template <bool FAST>
 struct FetchGated {
   const unsigned* list;
-  const double* P;       // field base (no offset applied)
-  const unsigned* dil;   // activity bitmap [rows][words]
+  const unsigned* dil;   // activity bitmap [rows][words], last word of every row always zero
+  unsigned listS, dilS;  // shared addresses of the same (FAST plan)
+  const double* P;       // field base (no offset applied), global
   double B2;
-  int pitch, words, dy, dx;
+  unsigned off;          // (dx << 16) + dy
+  int pitch, words;
   __device__ __forceinline__ void get(int k, double (&v)[GRP]) const {
-    const unsigned key = list[k];
-    const int xx = (int)(key >> 16) + dx, yy = (int)(key & 0xffffu) + dy;
-    const int wi = xx >> 5;
-    const unsigned* row = dil + yy * words;
-    const unsigned w0 = row[wi];
-    const unsigned w1 = (wi + 1 < words) ? row[wi + 1] : 0u;
-    const unsigned f = __funnelshift_r(w0, w1, xx & 31);
+    unsigned sxy, w0, w1;
+    if (FAST) {
+      sxy = lds_u32(listS + 4u * k) + off;
+    } else {
+      sxy = list[k] + off;
+    }
+    const unsigned xx = sxy >> 16, yy = sxy & 0xffffu;
+    const unsigned wi = yy * words + (xx >> 5);
+    if (FAST) {
+      w0 = lds_u32(dilS + 4u * wi);
+      w1 = lds_u32(dilS + 4u * wi + 4u);
+    } else {
+      w0 = dil[wi];
+      w1 = dil[wi + 1];
+    }
+    const unsigned f = __funnelshift_r(w0, w1, xx & 31u);
+    const double* q = P + (yy * pitch + xx);
 #pragma unroll
-    for (int g = 0; g < GRP; ++g) v[g] = B2;
-    if (f & ((1u << GRP) - 1u)) {
-      const double* q = P + yy * pitch + xx;
-#pragma unroll
-      for (int g = 0; g < GRP; ++g)
-        if ((f >> g) & 1u) v[g] = q[g];
+    for (int g = 0; g < GRP; ++g) {
+      double pv = B2;
+      if ((f >> g) & 1u) pv = __ldca(q + g);
+      v[g] = pv;
     }
   }
 };
@@ -130,12 +171,13 @@ __device__ __forceinline__ void leaf_sum_g(const F& f, int off, int n, double (&
   for (int l = 0; l < 8; ++l) f.get(off + l, r[l]);
   const int m = n - (n & 7);
   for (int i = 8; i < m; i += 8) {
+    double v[8][GRP];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) f.get(off + i + l, v[l]);       // eight independent gathers in flight
 #pragma unroll
     for (int l = 0; l < 8; ++l) {
-      double v[GRP];
-      f.get(off + i + l, v);
 #pragma unroll
-      for (int g = 0; g < GRP; ++g) r[l][g] = dadd(r[l][g], v[g]);
+      for (int g = 0; g < GRP; ++g) r[l][g] = dadd(r[l][g], v[l][g]);
     }
   }
 #pragma unroll
@@ -304,7 +346,9 @@ __device__ __forceinline__ void build_list(const double* dxs, const double* dys,
   int pos = incl - mine;
 #pragma unroll
   for (int e = 0; e < E; ++e) {
-    if (keep[e]) list[pos++] = key[e];
+    if (keep[e]) {
+      list[pos++] = key[e];
+    }
   }
   int total = __shfl_sync(FULL, incl, 31);
   if (lane == 0) *cnt = total;
@@ -329,14 +373,258 @@ __device__ __forceinline__ double block_min(double v, BlockScratch& bs) {
   return r;
 }
 
+
+// ---- separable blur (phase D) templated on the radius so every tap loop unrolls and its loads pipeline.
+// RT == 0: generic run-time radius.  Returns (through refs) the running minimum and the number of active cells.
+template <int RT, bool FAST, bool DENSE>
+__device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot, int Pp, int Wx, int Wy, int* counter,
+                                        double& mnOut, int& activeOut, double& thrOut) {
+  __shared__ double s_w[2 * SLAM_MAX_BLUR_RADIUS + 1];
+  __shared__ int s_active[NW];
+  const unsigned* bits = buf<FAST, unsigned>(S.oBits, gslot, S.gBits);
+  const unsigned* bitsT = buf<FAST, unsigned>(S.oBitsT, gslot, S.gBitsT);
+  unsigned* dil = buf<FAST, unsigned>(S.oDil, gslot, S.gDil);
+  double* Pf = DENSE ? sbuf<double>(S.oP) : reinterpret_cast<double*>(gslot + S.gP);
+  double* VwAll = sbuf<double>(S.oVw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = RT ? RT : S.r;
+  const int words = S.words, WT = S.WT;
+  if (tid <= 2 * r) s_w[tid] = S.w[tid];
+  int myActive = 0;
+  // D1. activity bitmap: cell (i, j) is active iff an occupied cell lies within +-r rows and +-r columns
+  //     (reflected taps always fall inside that span, so plain dilation is exact).
+  if (words <= 32) {
+    const int seg = words <= 16 ? 16 : 32;               // lanes per row
+    const int rowsPerWarp = 32 / seg;
+    const int sub = lane / seg, w = lane - sub * seg;
+    for (int i0 = warp * rowsPerWarp; i0 < Wy; i0 += NW * rowsPerWarp) {
+      const int i = i0 + sub;
+      unsigned v = 0u;
+      if (i < Wy && w < words) {
+#pragma unroll
+        for (int d = -r; d <= r; ++d) v |= bits[reflect_idx(i + d, Wy) * words + w];
+      }
+      unsigned lo = __shfl_up_sync(FULL, v, 1, seg), hi = __shfl_down_sync(FULL, v, 1, seg);
+      if (w == 0) lo = 0u;
+      if (w >= words - 1) hi = 0u;
+      unsigned dl = v;
+#pragma unroll
+      for (int k = 1; k <= r; ++k) dl |= (v << k) | (v >> k) | (lo >> (32 - k)) | (hi << (32 - k));
+      if (i < Wy && w < words) {
+        const int valid = Wx - 32 * w;                   // columns of this word that exist
+        if (valid < 32) dl &= valid <= 0 ? 0u : ((1u << valid) - 1u);
+        dil[i * words + w] = dl;
+        myActive += __popc(dl);
+      }
+    }
+  } else {
+    for (int t = tid; t < Wy * words; t += NT) {
+      const int i = t / words, w = t - i * words;
+      unsigned lo = 0u, v = 0u, hi = 0u;
+      for (int d = -r; d <= r; ++d) {
+        const unsigned* row = bits + reflect_idx(i + d, Wy) * words;
+        v |= row[w];
+        if (w > 0) lo |= row[w - 1];
+        if (w + 1 < words) hi |= row[w + 1];
+      }
+      unsigned dl = v;
+      for (int k = 1; k <= r; ++k) dl |= (v << k) | (v >> k) | (lo >> (32 - k)) | (hi << (32 - k));
+      const int valid = Wx - 32 * w;
+      if (valid < 32) dl &= valid <= 0 ? 0u : ((1u << valid) - 1u);
+      dil[t] = dl;
+      myActive += __popc(dl);
+    }
+  }
+  if (tid == 0) *counter = 0;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) myActive += __shfl_xor_sync(FULL, myActive, d);
+  if (lane == 0) s_active[warp] = myActive;
+  __syncthreads();
+  int nActive = 0;
+  for (int w2 = 0; w2 < NW; ++w2) nActive += s_active[w2];
+  // probMin (:43): every blurred value is >= the all-background value B2 (each operation is monotone in its inputs
+  // and the background has the lowest inputs), so as soon as one inactive cell exists probMin == B2 and the clamp
+  // threshold is known before the blur; otherwise the caller takes the minimum and clamps afterwards.
+  const bool anyInactive = nActive < Wx * Wy;
+  const double thr = anyInactive ? dmul(0.5, S.B2) : 1.0;   // field values are <= 0: 1.0 never clamps
+  const double* __restrict__ lut = S.lutV;
+  // D2. active tiles (32 columns x 1 row), two per warp at a time (independent dependency chains interleave).
+  //     First pass (axis 0) depends only on the 2r+1 occupancy bits of a column:
+  //       out = x[c]*w[r]; out += (x[c+j] + x[c-j])*w[j+r], j = -r..-1, with x in {log(missProb), 0}.
+  double mn = 0.0;
+  const int nTiles = Wy * words;
+  double* Vw = VwAll + warp * 128;
+  const unsigned patMask = (2u << (2 * r)) - 1u;
+  for (;;) {
+    int tb = 0;
+    if (lane == 0) tb = atomicAdd(counter, 32);
+    tb = __shfl_sync(FULL, tb, 0);
+    if (tb >= nTiles) break;
+    const int tmine = tb + lane;
+    const unsigned wmine = tmine < nTiles ? dil[tmine] : 0u;
+    unsigned am = __ballot_sync(FULL, wmine != 0u);
+    while (am) {
+      int tt[2];
+      unsigned dls[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (am) {
+          const int b = __ffs(am) - 1;
+          am &= am - 1;
+          tt[u] = tb + b;
+          dls[u] = __shfl_sync(FULL, wmine, b);
+        } else {
+          tt[u] = -1;
+          dls[u] = 0u;
+        }
+      }
+      int ti[2], tw[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        ti[u] = tt[u] < 0 ? 0 : tt[u] / words;
+        tw[u] = tt[u] < 0 ? 0 : tt[u] - ti[u] * words;
+      }
+      // virtual columns 32w-r .. 32w+31+r: lane handles vc0 = 32w-r+lane and (lane < 2r) vc1 = vc0+32
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = ti[u];
+          const int col = reflect_idx(32 * tw[u] - r + lane + 32 * h, Wx);
+          const unsigned* colBits = bitsT + col * WT;
+          unsigned sr;
+          if (i - r >= 0 && i + r < Wy) {       // the column's 2r+1 rows straight out of the transposed bitmap
+            const int lo = i - r;
+            sr = __funnelshift_r(colBits[lo >> 5], colBits[(lo >> 5) + 1], lo & 31) & patMask;
+          } else {                              // top / bottom border: reflected rows, bit by bit
+            sr = 0u;
+            for (int d = -r; d <= r; ++d) {
+              const int rr = reflect_idx(i + d, Wy);
+              sr |= ((colBits[rr >> 5] >> (rr & 31)) & 1u) << (d + r);
+            }
+          }
+          const double v = __ldg(lut + sr);     // first-pass value of this column pattern
+          if (h == 0 || lane < 2 * r) Vw[u * 64 + lane + 32 * h] = v;
+        }
+      }
+      __syncwarp();
+      // second pass (axis 1) for the active cells of the tiles
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if ((dls[u] >> lane) & 1u) {
+          const double* c = Vw + u * 64 + lane + r;       // virtual column of cell 32w+lane
+          double val = dmul(c[0], s_w[r]);
+#pragma unroll
+          for (int jj = 0; jj < r; ++jj) val = dadd(val, dmul(dadd(c[jj - r], c[r - jj]), s_w[jj]));
+          mn = fmin(mn, val);
+          Pf[(size_t)ti[u] * Pp + 32 * tw[u] + lane] = val > thr ? 0.0 : val;     // clamp (:44)
+        }
+      }
+      __syncwarp();
+    }
+  }
+  mnOut = mn;
+  activeOut = nActive;
+  thrOut = anyInactive ? thr : 0.0;     // 0.0 = "not clamped yet"
+}
+
+
+struct ScoreArgs {
+  unsigned char* gslot;
+  const double *rv, *tw;
+  double* dvol;
+  double B2, thr;
+  size_t gP, gDil, gScores;
+  int oLists, oCnt, oP, oDil, oScores, needScores;
+  int Kpad, Pp, words, nHalf, nOff, nt, t0;
+};
+
+// Score volume of a batch of thetas (phase G2).  Kept out of line so the hot gather loop gets its own register
+// allocation instead of inheriting the pressure of the rest of the fused kernel.
+template <bool FAST, bool DENSE>
+__device__ __noinline__ void score_batch(const ScoreArgs& A, double& bestIO, int& bestIdxIO, int& nanIO) {
+  const unsigned* lists = sbuf<unsigned>(A.oLists);
+  const int* cnts = sbuf<int>(A.oCnt);
+  const double* Pf = DENSE ? sbuf<double>(A.oP) : reinterpret_cast<const double*>(A.gslot + A.gP);
+  const unsigned* dil = buf<FAST, unsigned>(A.oDil, A.gslot, A.gDil);
+  double* scores = A.needScores ? buf<FAST, double>(A.oScores, A.gslot, A.gScores) : nullptr;
+  const int tid = threadIdx.x;
+  const int nOff = A.nOff, nOff2 = nOff * nOff;
+  const int nGrp = (nOff + GRP - 1) / GRP;
+  const int perTheta = nOff * nGrp;
+  const int nq = A.nt * perTheta;
+  double best = bestIO;
+  int bestIdx = bestIdxIO, sawNan = nanIO;
+  for (int q = tid; q < nq; q += NT) {
+    const int tl = q / perTheta, rem0 = q - tl * perTheta;
+    const int a = rem0 / nGrp, b0 = (rem0 - a * nGrp) * GRP;
+    double sc[GRP];
+    if (DENSE) {
+      FetchDense f;
+      f.listS = smem_u32(lists + tl * A.Kpad);
+      f.baseS = smem_u32(Pf);
+      f.off = (unsigned)(((b0 - A.nHalf) << 16) + (a - A.nHalf));
+      f.pitch = A.Pp;
+      pairwise_g(f, cnts[tl], sc);                                 // np.sum(axis=2) :130
+    } else {
+      FetchGated<FAST> f;
+      f.list = lists + tl * A.Kpad;
+      f.dil = dil;
+      f.listS = smem_u32(f.list);
+      f.dilS = FAST ? smem_u32(dil) : 0u;
+      f.P = Pf; f.B2 = A.B2; f.pitch = A.Pp; f.words = A.words;
+      f.off = (unsigned)(((b0 - A.nHalf) << 16) + (a - A.nHalf));
+      pairwise_g(f, cnts[tl], sc);
+    }
+#pragma unroll
+    for (int g = 0; g < GRP; ++g) {
+      const int b = b0 + g;
+      if (b < nOff) {
+        const int rem = a * nOff + b;
+        double v = sc[g];
+        if (A.rv) v = dadd(v, A.rv[rem]);                          // + rv + thetaWeight :131
+        if (A.tw) v = dadd(v, A.tw[rem]);
+        const int flat = (A.t0 + tl) * nOff2 + rem;
+        if (scores) scores[flat] = v;
+        if (A.dvol) A.dvol[flat] = v;
+        if (v != v) sawNan = 1;
+        if (bestIdx < 0 || v > best || (v == best && flat < bestIdx)) { best = v; bestIdx = flat; }
+      }
+    }
+  }
+  bestIO = best; bestIdxIO = bestIdx; nanIO = sawNan;
+}
+
+struct ListArgs {
+  const double *cosT, *sinT;
+  double ox, oy, bx, by, ul;
+  int oDx, oDy, oLists, oCnt;
+  int K0, nHalf, Wx, Wy, Kpad, nt, t0;
+};
+
+template <int E>
+__device__ __noinline__ void lists_batch(const ListArgs& A, int& statusIO) {
+  const double* dxs = sbuf<double>(A.oDx);
+  const double* dys = sbuf<double>(A.oDy);
+  unsigned* lists = sbuf<unsigned>(A.oLists);
+  int* cnts = sbuf<int>(A.oCnt);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int status = statusIO;
+  for (int tl = warp; tl < A.nt; tl += NW)
+    build_list<E>(dxs, dys, A.K0, A.ox, A.oy, A.cosT[A.t0 + tl], A.sinT[A.t0 + tl], A.bx, A.by, A.ul, A.nHalf,
+                  A.Wx, A.Wy, lists + tl * A.Kpad, cnts + tl, lane, status);
+  statusIO = status;
+}
+
 struct StageOut {
   double x, y, th, conf;
   int it, ia, ib;
 };
 
+template <bool FAST, bool DENSE>
 __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, int p, double cx, double cy, double cth,
-                          bool sample, double uniform, unsigned char* smem, unsigned char* gslot, BlockScratch& bs,
-                          int& status, StageOut& out, long long* cyc) {
+                          bool sample, double uniform, unsigned char* gslot, BlockScratch& bs, int& status,
+                          StageOut& out, long long* cyc) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double ul = S.unitLength;
   const int r = S.r;
@@ -356,16 +644,15 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
   const int words = S.words;
   const int nStrips = (Wx + 31) >> 5;
 
-  unsigned* bits = S.bitsInSmem ? (unsigned*)(smem + S.oBits) : (unsigned*)(gslot + S.gBits);
-  unsigned* bitsT = S.bitsInSmem ? (unsigned*)(smem + S.oBitsT) : (unsigned*)(gslot + S.gBitsT);  // [col][WT] transposed
-  unsigned* dil = S.bitsInSmem ? (unsigned*)(smem + S.oDil) : (unsigned*)(gslot + S.gDil);   // activity bitmap
+  unsigned* bits = buf<FAST, unsigned>(S.oBits, gslot, S.gBits);
+  unsigned* bitsT = buf<FAST, unsigned>(S.oBitsT, gslot, S.gBitsT);    // [col][WT] transposed
+  unsigned* dil = buf<FAST, unsigned>(S.oDil, gslot, S.gDil);         // activity bitmap
   const int WT = S.WT;
-  double* Vw = (double*)(smem + S.oVw) + warp * 64;  // per-warp scratch: first-pass values of a tile + halo
-  short* rowMap = (short*)(smem + S.oRow);
-  short* colMap = (short*)(smem + S.oCol);
-  double* Pf = S.PInSmem ? (double*)(smem + S.oP) : (double*)(gslot + S.gP);
+  short* rowMap = sbuf<short>(S.oRow);
+  short* colMap = sbuf<short>(S.oCol);
+  double* Pf = DENSE ? sbuf<double>(S.oP) : reinterpret_cast<double*>(gslot + S.gP);
   const int Pp = S.Ppitch;
-  const bool dense = S.PInSmem != 0;                 // coarse: dense field in shared memory, ungated gathers
+  constexpr bool dense = DENSE;                      // coarse: dense field in shared memory, ungated gathers
 
   __syncthreads();  // previous users of the arena are done
   if (cyc && tid == 0) cyc[0] -= clock64();
@@ -427,129 +714,35 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
   if (cyc && tid == 0) { long long t = clock64(); cyc[0] += t; cyc[1] -= t; }
 
   // ---- D. separable blur in scipy's order, only where the result can differ from the background.
-  // D1. activity bitmap: cell (i, j) is active iff an occupied cell lies within +-r rows and +-r columns
-  //     (reflected taps always fall inside that span, so plain dilation is exact).
-  {
-    const int seg = words <= 16 ? 16 : 32;               // lanes per row
-    if (words <= 32) {
-      const int rowsPerWarp = 32 / seg;
-      const int sub = lane / seg, w = lane - sub * seg;
-      for (int i0 = warp * rowsPerWarp; i0 < Wy; i0 += NW * rowsPerWarp) {
-        const int i = i0 + sub;
-        unsigned v = 0u;
-        if (i < Wy && w < words)
-          for (int d = -r; d <= r; ++d) v |= bits[reflect_idx(i + d, Wy) * words + w];
-        unsigned lo = __shfl_up_sync(FULL, v, 1, seg), hi = __shfl_down_sync(FULL, v, 1, seg);
-        if (w == 0) lo = 0u;
-        if (w >= words - 1) hi = 0u;
-        unsigned dl = v;
-        for (int k = 1; k <= r; ++k) dl |= (v << k) | (v >> k) | (lo >> (32 - k)) | (hi << (32 - k));
-        if (i < Wy && w < words) {
-          const int valid = Wx - 32 * w;                 // columns of this word that exist
-          if (valid < 32) dl &= valid <= 0 ? 0u : ((1u << valid) - 1u);
-          dil[i * words + w] = dl;
-        }
-      }
-    } else {
-      for (int t = tid; t < Wy * words; t += NT) {
-        const int i = t / words, w = t - i * words;
-        unsigned lo = 0u, v = 0u, hi = 0u;
-        for (int d = -r; d <= r; ++d) {
-          const unsigned* row = bits + reflect_idx(i + d, Wy) * words;
-          v |= row[w];
-          if (w > 0) lo |= row[w - 1];
-          if (w + 1 < words) hi |= row[w + 1];
-        }
-        unsigned dl = v;
-        for (int k = 1; k <= r; ++k) dl |= (v << k) | (v >> k) | (lo >> (32 - k)) | (hi << (32 - k));
-        const int valid = Wx - 32 * w;
-        if (valid < 32) dl &= valid <= 0 ? 0u : ((1u << valid) - 1u);
-        dil[t] = dl;
-      }
-    }
-  }
-  __syncthreads();
-  // D2. blur the active tiles (32 columns x 1 row).  First pass (axis 0) depends only on the 2r+1 occupancy bits
-  //     of a column: out = x[c]*w[r]; out += (x[c+j] + x[c-j])*w[j+r], j = -r..-1, with x in {log(missProb), 0}.
   double mn = 0.0;                 // every field value is <= 0
-  int nActive = 0;                 // active cells seen by this thread's warp (lane 0 keeps the count)
-  const int nTiles = Wy * words;
-  for (int tb = warp * 32; tb < nTiles; tb += NW * 32) {
-    const int tmine = tb + lane;
-    const unsigned wmine = tmine < nTiles ? dil[tmine] : 0u;
-    unsigned am = __ballot_sync(FULL, wmine != 0u);
-    while (am) {
-      const int b = __ffs(am) - 1;
-      am &= am - 1;
-      const unsigned dl = __shfl_sync(FULL, wmine, b);
-      const int t = tb + b;
-      const int i = t / words, w = t - i * words;
-      // virtual columns 32w-r .. 32w+31+r; lane handles vc0 = 32w-r+lane and (lane < 2r) vc1 = vc0+32
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (h == 1 && lane >= 2 * r) break;
-        const int col = reflect_idx(32 * w - r + lane + 32 * h, Wx);
-        const unsigned* colBits = bitsT + col * WT;
-        unsigned sr;
-        if (i - r >= 0 && i + r < Wy) {         // the column's 2r+1 rows straight out of the transposed bitmap
-          const int lo = i - r;
-          sr = __funnelshift_r(colBits[lo >> 5], colBits[(lo >> 5) + 1], lo & 31) & ((2u << (2 * r)) - 1u);
-        } else {                                // top / bottom border: reflected rows, bit by bit
-          sr = 0u;
-          for (int d = -r; d <= r; ++d) {
-            const int rr = reflect_idx(i + d, Wy);
-            sr |= ((colBits[rr >> 5] >> (rr & 31)) & 1u) << (d + r);
-          }
-        }
-        double v = S.B1;
-        if (sr != 0u) {
-          v = ((sr >> r) & 1u) ? 0.0 : S.C0;
-          for (int jj = 0; jj < r; ++jj) {
-            const int occ = (int)((sr >> jj) & 1u) + (int)((sr >> (2 * r - jj)) & 1u);
-            const double tt = occ == 0 ? S.T2[jj] : (occ == 1 ? S.T1[jj] : 0.0);
-            v = dadd(v, tt);
-          }
-        }
-        Vw[lane + 32 * h] = v;
-      }
-      __syncwarp();
-      // second pass (axis 1) for the active cells of the tile
-      if ((dl >> lane) & 1u) {
-        const double* c = Vw + lane + r;          // virtual column of cell 32w+lane
-        double val = dmul(c[0], S.w[r]);
-        for (int jj = 0; jj < r; ++jj) val = dadd(val, dmul(dadd(c[jj - r], c[r - jj]), S.w[jj]));
-        Pf[(size_t)i * Pp + 32 * w + lane] = val;
-        mn = fmin(mn, val);
-      }
-      if (lane == 0) nActive += __popc(dl);
-      __syncwarp();
+  int nActive = 0;
+  double thr = 0.0;
+  {
+    int* counter = &bs.ibcast[4];
+    switch (r) {
+      case 2: blur_stage<2, FAST, DENSE>(S, gslot, Pp, Wx, Wy, counter, mn, nActive, thr); break;
+      case 4: blur_stage<4, FAST, DENSE>(S, gslot, Pp, Wx, Wy, counter, mn, nActive, thr); break;
+      case 8: blur_stage<8, FAST, DENSE>(S, gslot, Pp, Wx, Wy, counter, mn, nActive, thr); break;
+      default: blur_stage<0, FAST, DENSE>(S, gslot, Pp, Wx, Wy, counter, mn, nActive, thr); break;
     }
   }
-  // ---- E. probMin, clamp (:43-44).  Inactive cells hold exactly B2 (the minimum of the value set).
-  if (lane == 0) bs.ival[warp] = nActive;
-  __syncthreads();
-  int activeCells = 0;
-  for (int w2 = 0; w2 < NW; ++w2) activeCells += bs.ival[w2];
-  if (activeCells < Wx * Wy) mn = fmin(mn, S.B2);
-  const double probMin = block_min(mn, bs);
-  const double thr = dmul(0.5, probMin);
-  for (int tb = warp * 32; tb < nTiles; tb += NW * 32) {
-    const int tmine = tb + lane;
-    const unsigned wmine = tmine < nTiles ? dil[tmine] : 0u;
-    unsigned am = __ballot_sync(FULL, wmine != 0u);
-    while (am) {
-      const int b = __ffs(am) - 1;
-      am &= am - 1;
-      const unsigned dl = __shfl_sync(FULL, wmine, b);
-      const int t = tb + b;
-      const int i = t / words, w = t - i * words;
-      if ((dl >> lane) & 1u) {
-        double* q = Pf + (size_t)i * Pp + 32 * w + lane;
-        if (*q > thr) *q = 0.0;
+  // ---- E. probMin, clamp (:43-44).  Normally done inside the blur (probMin == B2); only a window without a single
+  //         background cell needs the explicit minimum + a second pass.
+  {
+    const double probMin = block_min(mn, bs);          // also the barrier that publishes the field
+    if (probMin < S.B2) status |= SLAM_ST_INDEX_OUT_OF_FIELD;   // cannot happen (monotone rounding); fail loudly
+    if (thr == 0.0) {
+      thr = dmul(0.5, probMin);
+      for (int i = tid; i < Wy * Wx; i += NT) {
+        const int yy = i / Wx, xx = i - yy * Wx;
+        if ((dil[yy * words + (xx >> 5)] >> (xx & 31)) & 1u) {
+          double* q = Pf + (size_t)yy * Pp + xx;
+          if (*q > thr) *q = 0.0;
+        }
       }
+      __syncthreads();
     }
   }
-  __syncthreads();
   if (cyc && tid == 0) { long long t = clock64(); cyc[1] += t; cyc[2] -= t; }
   if (P.dbgProb[stageId]) {
     double* d = P.dbgProb[stageId] + (size_t)p * S.Wmax * S.Wmax;
@@ -562,8 +755,8 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
   }
 
   // ---- F. beam end points (:81-89) with order-preserving compaction of beams < maxRange
-  double* dxs = (double*)(smem + S.oDx);
-  double* dys = (double*)(smem + S.oDy);
+  double* dxs = sbuf<double>(S.oDx);
+  double* dys = sbuf<double>(S.oDy);
   int K0;
   {
     const int K = P.K;
@@ -603,70 +796,42 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
 
   if (cyc && tid == 0) cyc[2] += clock64();
   // ---- G. per-theta lists + score volume, TB thetas at a time
-  unsigned* lists = (unsigned*)(smem + S.oLists);
-  int* cnts = (int*)(smem + S.oCnt);
-  double* scores = S.needScores ? (S.scoresInSmem ? (double*)(smem + S.oScores) : (double*)(gslot + S.gScores)) : nullptr;
+  double* scores = S.needScores ? buf<FAST, double>(S.oScores, gslot, S.gScores) : nullptr;
   double* dvol = P.dbgVol[stageId] ? P.dbgVol[stageId] + (size_t)p * S.nPoses : nullptr;
   const int nOff = S.nOff, nOff2 = nOff * nOff;
   const double* rv = (stageId == 0) ? P.rv : nullptr;
   const double* tw = (stageId == 0 && P.tw) ? P.tw + (size_t)p * nOff2 : nullptr;
   double best = 0.0;
   int bestIdx = -1;
-  bool sawNan = false;
+  int sawNan = 0;
+  ScoreArgs SA;
+  SA.gslot = gslot; SA.rv = rv; SA.tw = tw; SA.dvol = dvol; SA.B2 = S.B2; SA.thr = thr;
+  SA.gP = S.gP; SA.gDil = S.gDil; SA.gScores = S.gScores;
+  SA.oLists = S.oLists; SA.oCnt = S.oCnt; SA.oP = S.oP; SA.oDil = S.oDil; SA.oScores = S.oScores;
+  SA.needScores = S.needScores;
+  SA.Kpad = S.Kpad; SA.Pp = Pp; SA.words = words; SA.nHalf = S.nHalf; SA.nOff = nOff;
+  ListArgs LA;
+  LA.cosT = S.cosT; LA.sinT = S.sinT;
+  LA.ox = cx; LA.oy = cy; LA.bx = xr0; LA.by = yr0; LA.ul = ul;
+  LA.oDx = S.oDx; LA.oDy = S.oDy; LA.oLists = S.oLists; LA.oCnt = S.oCnt;
+  LA.K0 = K0; LA.nHalf = S.nHalf; LA.Wx = Wx; LA.Wy = Wy; LA.Kpad = S.Kpad;
   for (int t0 = 0; t0 < S.nTheta; t0 += S.TB) {
     const int nt = min(S.TB, S.nTheta - t0);
     if (cyc && tid == 0) cyc[3] -= clock64();
-    for (int tl = warp; tl < nt; tl += NW) {
-      const double c = S.cosT[t0 + tl], s = S.sinT[t0 + tl];
-      if (S.E == 8)
-        build_list<8>(dxs, dys, K0, cx, cy, c, s, xr0, yr0, ul, S.nHalf, Wx, Wy, lists + tl * S.Kpad, cnts + tl, lane, status);
-      else
-        build_list<16>(dxs, dys, K0, cx, cy, c, s, xr0, yr0, ul, S.nHalf, Wx, Wy, lists + tl * S.Kpad, cnts + tl, lane, status);
-    }
+    LA.nt = nt; LA.t0 = t0;
+    if (S.E == 8) lists_batch<8>(LA, status);
+    else lists_batch<16>(LA, status);
     __syncthreads();
     if (cyc && tid == 0) { long long t = clock64(); cyc[3] += t; cyc[4] -= t; }
-    const int nGrp = (nOff + GRP - 1) / GRP;
-    const int nq = nt * nOff * nGrp;
-    for (int q = tid; q < nq; q += NT) {
-      const int tl = q / (nOff * nGrp), rem0 = q - tl * (nOff * nGrp);
-      const int a = rem0 / nGrp, b0 = (rem0 - a * nGrp) * GRP;
-      double sc[GRP];
-      if (dense) {
-        FetchDense f;
-        f.list = lists + tl * S.Kpad;
-        f.base = Pf + (a - S.nHalf) * Pp + (b0 - S.nHalf);
-        f.pitch = Pp;
-        pairwise_g(f, cnts[tl], sc);                               // np.sum(axis=2) :130
-      } else {
-        FetchGated f;
-        f.list = lists + tl * S.Kpad;
-        f.P = Pf; f.dil = dil; f.B2 = S.B2; f.pitch = Pp; f.words = words;
-        f.dy = a - S.nHalf; f.dx = b0 - S.nHalf;
-        pairwise_g(f, cnts[tl], sc);
-      }
-#pragma unroll
-      for (int g = 0; g < GRP; ++g) {
-        const int b = b0 + g;
-        if (b < nOff) {
-          const int rem = a * nOff + b;
-          double v = sc[g];
-          if (rv) v = dadd(v, rv[rem]);                            // + rv + thetaWeight :131
-          if (tw) v = dadd(v, tw[rem]);
-          const int flat = (t0 + tl) * nOff2 + rem;
-          if (scores) scores[flat] = v;
-          if (dvol) dvol[flat] = v;
-          if (v != v) sawNan = true;
-          if (bestIdx < 0 || v > best || (v == best && flat < bestIdx)) { best = v; bestIdx = flat; }
-        }
-      }
-    }
+    SA.nt = nt; SA.t0 = t0;
+    score_batch<FAST, DENSE>(SA, best, bestIdx, sawNan);
     __syncthreads();
     if (cyc && tid == 0) cyc[4] += clock64();
   }
   if (cyc && tid == 0) cyc[5] -= clock64();
 
   // ---- H. select (:133-141)
-  if (__syncthreads_or(sawNan ? 1 : 0)) status |= SLAM_ST_NAN_SCORE;
+  if (__syncthreads_or(sawNan)) status |= SLAM_ST_NAN_SCORE;
   int chosen;
   {  // first maximum in C order
 #pragma unroll
@@ -692,7 +857,7 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
     const int n = S.nPoses;
     for (int i = tid; i < n; i += NT) scores[i] = exp(scores[i]);
     __syncthreads();
-    double* leafSum = (double*)(smem + S.oLeaf);
+    double* leafSum = sbuf<double>(S.oLeaf);
     SmemVal sv;
     sv.a = scores;
     for (int l = tid; l < S.nLeaves; l += NT) {
@@ -788,7 +953,6 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
 }
 
 __global__ void __launch_bounds__(NT, 1) match_kernel(const __grid_constant__ MatchParams P) {
-  extern __shared__ __align__(16) unsigned char smem[];
   __shared__ BlockScratch bs;
   unsigned char* gslot = P.scratch + (size_t)blockIdx.x * P.slotBytes;
   long long* cyc = P.dbgCycles ? P.dbgCycles + (size_t)blockIdx.x * 16 : nullptr;
@@ -797,8 +961,15 @@ __global__ void __launch_bounds__(NT, 1) match_kernel(const __grid_constant__ Ma
     int status = 0;
     StageOut c, f;
     const bool sample = P.uniforms != nullptr;
-    run_stage(P, P.st[0], 0, p, x, y, th, sample, sample ? P.uniforms[p] : 0.0, smem, gslot, bs, status, c, cyc);
-    run_stage(P, P.st[1], 1, p, c.x, c.y, c.th, false, 0.0, smem, gslot, bs, status, f, cyc ? cyc + 8 : nullptr);
+    const double u = sample ? P.uniforms[p] : 0.0;
+    long long* cyc2 = cyc ? cyc + 8 : nullptr;
+    if (P.fast) {      // everything but the sparse fine field lives in shared memory
+      run_stage<true, true>(P, P.st[0], 0, p, x, y, th, sample, u, gslot, bs, status, c, cyc);
+      run_stage<true, false>(P, P.st[1], 1, p, c.x, c.y, c.th, false, 0.0, gslot, bs, status, f, cyc2);
+    } else {           // large windows: bitmaps / fields / scores in the global slot
+      run_stage<false, false>(P, P.st[0], 0, p, x, y, th, sample, u, gslot, bs, status, c, cyc);
+      run_stage<false, false>(P, P.st[1], 1, p, c.x, c.y, c.th, false, 0.0, gslot, bs, status, f, cyc2);
+    }
     status = __syncthreads_or(status);
     if (threadIdx.x == 0) {
       P.outPose[3 * p] = f.x; P.outPose[3 * p + 1] = f.y; P.outPose[3 * p + 2] = f.th;
@@ -808,6 +979,19 @@ __global__ void __launch_bounds__(NT, 1) match_kernel(const __grid_constant__ Ma
       P.status[p] = status;
     }
   }
+}
+
+// First-pass (axis 0) value for every occupancy pattern of a column's 2r+1 rows; same operation order as scipy:
+// out = x[c]*w[r]; out += (x[c+j] + x[c-j])*w[j+r] for j = -r..-1 with x = 0 (occupied) or log(missProb).
+__global__ void lut_kernel(double* lut, int r, double C0, const double* T1, const double* T2) {
+  const unsigned sr = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sr >= (2u << (2 * r))) return;
+  double v = ((sr >> r) & 1u) ? 0.0 : C0;
+  for (int jj = 0; jj < r; ++jj) {
+    const int occ = (int)((sr >> jj) & 1u) + (int)((sr >> (2 * r - jj)) & 1u);
+    v = dadd(v, occ == 0 ? T2[jj] : (occ == 1 ? T1[jj] : 0.0));
+  }
+  lut[sr] = v;
 }
 
 // heading prior (ScanMatcher_OGBased.py:105-108)
@@ -866,9 +1050,10 @@ static int upload(slam_matcher* m, const T* h, size_t n, const T** d) {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static int plan_stage(slam_matcher* m, const slam_geometry* g, const slam_stage_desc& d, double R, int stageId,
-                      StageDev& S, size_t& smemNeed, size_t& slotBytes, size_t smemBudget) {
+                      StageDev& S, size_t& smemNeed, size_t& slotBytes, size_t smemBudget, bool fast, bool uploadTables) {
   if (d.blurRadius < 1 || d.blurRadius > SLAM_MAX_BLUR_RADIUS) return fail(SLAM_E_UNSUPPORTED, "blur radius must be 1..8");
   if (g->K < 2 || g->K > SLAM_MAX_BEAMS) return fail(SLAM_E_UNSUPPORTED, "beams per scan must be 2..512");
+  if (d.nHalf < 0 || d.nHalf > 15) return fail(SLAM_E_UNSUPPORTED, "search half-width must be 0..15 cells");
   S.unitLength = d.unitLength;
   S.logMiss = d.logMiss;
   S.r = d.blurRadius;
@@ -898,22 +1083,36 @@ static int plan_stage(slam_matcher* m, const slam_geometry* g, const slam_stage_
   S.nOff = 2 * d.nHalf + 1;
   S.nTheta = d.nTheta;
   S.nPoses = S.nTheta * S.nOff * S.nOff;
-  if (upload(m, d.h_thetas, d.nTheta, &S.thetas) || upload(m, d.h_cos, d.nTheta, &S.cosT) ||
-      upload(m, d.h_sin, d.nTheta, &S.sinT))
+  (void)uploadTables;
+  if (!S.thetas && (upload(m, d.h_thetas, d.nTheta, &S.thetas) || upload(m, d.h_cos, d.nTheta, &S.cosT) ||
+                    upload(m, d.h_sin, d.nTheta, &S.sinT)))
     return 1;
+  if (!S.lutV) {
+    const size_t n = (size_t)2 << (2 * r);
+    void* lut = nullptr;
+    SLAM_CUDA(cudaMalloc(&lut, n * sizeof(double)));
+    m->owned.push_back(lut);
+    const double *dT1 = nullptr, *dT2 = nullptr;
+    if (upload(m, S.T1, SLAM_MAX_BLUR_RADIUS, &dT1) || upload(m, S.T2, SLAM_MAX_BLUR_RADIUS, &dT2)) return 1;
+    lut_kernel<<<(unsigned)((n + 255) / 256), 256>>>((double*)lut, r, S.C0, dT1, dT2);
+    SLAM_CUDA(cudaGetLastError());
+    SLAM_CUDA(cudaDeviceSynchronize());
+    S.lutV = (const double*)lut;
+  }
   std::vector<int2> leaves;
   std::vector<short> prog;
   leaves_rec(0, S.nPoses, leaves, prog);
   if (leaves.size() > 30000) return fail(SLAM_E_UNSUPPORTED, "score volume too large");
   S.nLeaves = (int)leaves.size();
   S.progLen = (int)prog.size();
-  if (upload(m, leaves.data(), leaves.size(), &S.leaves) || upload(m, prog.data(), prog.size(), &S.prog)) return 1;
+  if (!S.leaves && (upload(m, leaves.data(), leaves.size(), &S.leaves) || upload(m, prog.data(), prog.size(), &S.prog)))
+    return 1;
 
   // ---- memory plan
   S.Wmax = (int)(2.0 * R / d.unitLength) + 2;
   S.Wmap = (int)(2.0 * R / g->unit) + 3;
   if (S.Wmax > 32000 || S.Wmap > 32000) return fail(SLAM_E_UNSUPPORTED, "search window too large");
-  S.words = (S.Wmax + GRP + 31) / 32;
+  S.words = (S.Wmax + GRP) / 32 + 2;      // >= 1 always-zero spare word per row (two-word funnel reads)
   S.WT = (S.Wmax + 31) / 32 + 1;
   if (S.WT % 2 == 0) S.WT += 1;          // odd column pitch: conflict-free transposed-bitmap reads
   S.Kpad = (g->K + 3) & ~3;
@@ -933,48 +1132,47 @@ static int plan_stage(slam_matcher* m, const slam_geometry* g, const slam_stage_
     pp = (pp + 3) & ~3;
   S.Ppitch = pp;
   const size_t PBytes = (size_t)(S.Wmax + 1) * S.Ppitch * 8;   // one slack row: grouped gathers may overshoot
-  // try placements from fastest to most frugal
-  for (int attempt = 0; attempt < 8; ++attempt) {
-    S.PInSmem = (attempt & 4) ? 0 : (stageId == 0);     // fine field: sparse, in the global slot (L2)
-    S.scoresInSmem = (attempt & 2) ? 0 : 1;
-    S.bitsInSmem = (attempt & 1) ? 0 : 1;
-    for (int TB : {S.nTheta, (S.nTheta + 1) / 2, NW, 8, 4}) {
-      if (TB > S.nTheta || TB < 1) continue;
-      S.TB = TB;
-      size_t off = 0;
-      auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return (int)o; };
-      S.oP = S.PInSmem ? take(PBytes) : 0;
-      S.oDil = S.bitsInSmem ? take(bitsBytes) : 0;      // activity bitmap lives through the correlation
-      S.oDx = take(dxyBytes);
-      S.oDy = take(dxyBytes);
-      S.oVw = take((size_t)NW * 64 * 8);
-      const size_t common = off;
-      // window / blur-phase buffers
-      S.oBits = S.bitsInSmem ? take(bitsBytes) : 0;
-      S.oBitsT = S.bitsInSmem ? take(bitsTBytes) : 0;
-      S.oRow = take(mapBytes);
-      S.oCol = take(mapBytes);
-      const size_t blurEnd = off;
-      // correlate-phase buffers alias the blur-phase ones
-      off = common;
-      S.oLists = take((size_t)TB * S.Kpad * 4);
-      S.oCnt = take((size_t)TB * 4);
-      S.oScores = (S.needScores && S.scoresInSmem) ? take(scoreBytes) : 0;
-      S.oLeaf = take(leafBytes);
-      const size_t need = std::max(blurEnd, off);
-      if (need <= smemBudget) {
-        smemNeed = std::max(smemNeed, need);
-        size_t g0 = slotBytes;
-        S.gBits = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsBytes, 256);
-        S.gBitsT = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsTBytes, 256);
-        S.gDil = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsBytes, 256);
-        S.gP = g0; g0 += S.PInSmem ? 0 : align_up(PBytes, 256);
-        S.gScores = g0; g0 += (S.needScores && !S.scoresInSmem) ? align_up(scoreBytes, 256) : 0;
-        slotBytes = g0;
-        return 0;
-      }
+  // FAST plan: bitmaps, lists, scores (and the dense coarse field) in shared memory; SLOW plan: global slot.
+  S.PInSmem = fast ? (stageId == 0) : 0;
+  S.scoresInSmem = fast ? 1 : 0;
+  S.bitsInSmem = fast ? 1 : 0;
+  for (int TB : {S.nTheta, (S.nTheta + 1) / 2, NW, 8, 4}) {
+    if (TB > S.nTheta || TB < 1) continue;
+    S.TB = TB;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return (int)o; };
+    S.oP = S.PInSmem ? take(PBytes) : 0;
+    S.oDil = S.bitsInSmem ? take(bitsBytes) : 0;      // activity bitmap lives through the correlation
+    S.oDx = take(dxyBytes);
+    S.oDy = take(dxyBytes);
+    S.oVw = take((size_t)NW * 128 * 8);
+    const size_t common = off;
+    // window / blur-phase buffers
+    S.oBits = S.bitsInSmem ? take(bitsBytes) : 0;
+    S.oBitsT = S.bitsInSmem ? take(bitsTBytes) : 0;
+    S.oRow = take(mapBytes);
+    S.oCol = take(mapBytes);
+    const size_t blurEnd = off;
+    // correlate-phase buffers alias the blur-phase ones
+    off = common;
+    S.oLists = take((size_t)TB * S.Kpad * 4);
+    S.oCnt = take((size_t)TB * 4);
+    S.oScores = (S.needScores && S.scoresInSmem) ? take(scoreBytes) : 0;
+    S.oLeaf = take(leafBytes);
+    const size_t need = std::max(blurEnd, off);
+    if (need <= smemBudget) {
+      smemNeed = std::max(smemNeed, need);
+      size_t g0 = slotBytes;
+      S.gBits = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsBytes, 256);
+      S.gBitsT = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsTBytes, 256);
+      S.gDil = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsBytes, 256);
+      S.gP = g0; g0 += S.PInSmem ? 0 : align_up(PBytes, 256);
+      S.gScores = g0; g0 += (S.needScores && !S.scoresInSmem) ? align_up(scoreBytes, 256) : 0;
+      slotBytes = g0;
+      return 0;
     }
   }
+  if (fast) return -1;   // caller retries with the global-slot plan
   return fail(SLAM_E_UNSUPPORTED, "stage does not fit the shared-memory plan");
 }
 
@@ -1000,10 +1198,19 @@ extern "C" int slam_matcher_create(const slam_geometry* g, const slam_matcher_de
   }
   const size_t budget = (size_t)smemMax - 1024;   // static shared + reserve
   size_t smemNeed = 0, slot = 0;
-  for (int s = 0; s < 2; ++s) {
-    int rc = plan_stage(m, g, s == 0 ? d->coarse : d->fine, d->windowRadius, s, P.st[s], smemNeed, slot, budget);
-    if (rc) { slam_matcher_destroy(m); return rc; }
+  bool fast = true;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    smemNeed = 0; slot = 0;
+    int rc = 0;
+    for (int s = 0; s < 2 && rc == 0; ++s)
+      rc = plan_stage(m, g, s == 0 ? d->coarse : d->fine, d->windowRadius, s, P.st[s], smemNeed, slot, budget, fast,
+                      attempt == 0);
+    if (rc == 0) break;
+    if (rc < 0 && fast) { fast = false; continue; }
+    slam_matcher_destroy(m);
+    return rc;
   }
+  P.fast = fast ? 1 : 0;
   m->smemBytes = smemNeed;
   P.slotBytes = align_up(slot, 256);
   m->numCtas = sms;
