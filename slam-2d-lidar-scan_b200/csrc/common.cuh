@@ -28,7 +28,7 @@ __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a,
 // streaming 16-byte load that does not pollute L1 (grid windows are read once per stage)
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p));
   return v;

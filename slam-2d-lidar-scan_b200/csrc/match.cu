@@ -23,9 +23,23 @@
 
 namespace slam {
 
-constexpr int NT = 512;       // threads per CTA
-constexpr int NW = NT / 32;   // warps per CTA
+constexpr int NT = 512;          // threads per CTA
+constexpr int NW = NT / 32;      // warps per CTA
+constexpr int NWC = NW;          // compute warps (all of them; a dedicated streaming warp could not keep up)
+constexpr int NTC = NWC * 32;    // compute threads
 constexpr unsigned FULL = 0xffffffffu;
+
+// barrier over the compute warps (named barrier 1)
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory"); }
+__device__ __forceinline__ int csync_or(int pred) {
+  int r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, 1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "r"(pred), "n"(NTC)
+      : "memory");
+  return r;
+}
 
 struct StageDev {
   double unitLength, logMiss;
@@ -65,6 +79,13 @@ struct MatchParams {
   long long* dbgCycles;  // [gridDim][16] or null
   int forceExactCdf;
   int fast;              // plan: 1 = shared-memory plan for both stages, 0 = global-slot plan
+  // background window stream (union of the coarse and every possible fine window, read once)
+  double RU;             // union half size = R + coarse search radius + margin
+  int UWcells;           // max columns of a union row segment (even)
+  int UW;                // bitmap words per union row = 2*ceil(UWcells/64) (even/odd bit planes per 64 cells)
+  int URows;             // max union rows
+  int ringRows, oRing;   // rows per ring stage, shared-memory offset of the 2-stage ring
+  size_t gU;             // offset of the two union bitmaps inside a CTA's global slot
 };
 
 // ------------------------------------------------------------------------------------------------ device
@@ -355,8 +376,8 @@ __device__ __forceinline__ void build_list(const double* dxs, const double* dys,
 }
 
 struct BlockScratch {
-  double dval[NW];
-  int ival[NW];
+  double dval[NWC];
+  int ival[NWC];
   double bcast[4];
   int ibcast[8];
 };
@@ -365,11 +386,11 @@ __device__ __forceinline__ double block_min(double v, BlockScratch& bs) {
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, d));
-  __syncthreads();
+  csync();
   if (lane == 0) bs.dval[warp] = v;
-  __syncthreads();
+  csync();
   double r = bs.dval[0];
-  for (int i = 1; i < NW; ++i) r = fmin(r, bs.dval[i]);
+  for (int i = 1; i < NWC; ++i) r = fmin(r, bs.dval[i]);
   return r;
 }
 
@@ -380,7 +401,7 @@ template <int RT, bool FAST, bool DENSE>
 __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot, int Pp, int Wx, int Wy, int* counter,
                                         double& mnOut, int& activeOut, double& thrOut) {
   __shared__ double s_w[2 * SLAM_MAX_BLUR_RADIUS + 1];
-  __shared__ int s_active[NW];
+  __shared__ int s_active[NWC];
   const unsigned* bits = buf<FAST, unsigned>(S.oBits, gslot, S.gBits);
   const unsigned* bitsT = buf<FAST, unsigned>(S.oBitsT, gslot, S.gBitsT);
   unsigned* dil = buf<FAST, unsigned>(S.oDil, gslot, S.gDil);
@@ -397,7 +418,7 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
     const int seg = words <= 16 ? 16 : 32;               // lanes per row
     const int rowsPerWarp = 32 / seg;
     const int sub = lane / seg, w = lane - sub * seg;
-    for (int i0 = warp * rowsPerWarp; i0 < Wy; i0 += NW * rowsPerWarp) {
+    for (int i0 = warp * rowsPerWarp; i0 < Wy; i0 += NWC * rowsPerWarp) {
       const int i = i0 + sub;
       unsigned v = 0u;
       if (i < Wy && w < words) {
@@ -418,7 +439,7 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
       }
     }
   } else {
-    for (int t = tid; t < Wy * words; t += NT) {
+    for (int t = tid; t < Wy * words; t += NTC) {
       const int i = t / words, w = t - i * words;
       unsigned lo = 0u, v = 0u, hi = 0u;
       for (int d = -r; d <= r; ++d) {
@@ -439,9 +460,9 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) myActive += __shfl_xor_sync(FULL, myActive, d);
   if (lane == 0) s_active[warp] = myActive;
-  __syncthreads();
+  csync();
   int nActive = 0;
-  for (int w2 = 0; w2 < NW; ++w2) nActive += s_active[w2];
+  for (int w2 = 0; w2 < NWC; ++w2) nActive += s_active[w2];
   // probMin (:43): every blurred value is >= the all-background value B2 (each operation is monotone in its inputs
   // and the background has the lowest inputs), so as soon as one inactive cell exists probMin == B2 and the clamp
   // threshold is known before the blur; otherwise the caller takes the minimum and clamps afterwards.
@@ -555,7 +576,7 @@ __device__ __noinline__ void score_batch(const ScoreArgs& A, double& bestIO, int
   const int nq = A.nt * perTheta;
   double best = bestIO;
   int bestIdx = bestIdxIO, sawNan = nanIO;
-  for (int q = tid; q < nq; q += NT) {
+  for (int q = tid; q < nq; q += NTC) {
     const int tl = q / perTheta, rem0 = q - tl * perTheta;
     const int a = rem0 / nGrp, b0 = (rem0 - a * nGrp) * GRP;
     double sc[GRP];
@@ -610,10 +631,72 @@ __device__ __noinline__ void lists_batch(const ListArgs& A, int& statusIO) {
   int* cnts = sbuf<int>(A.oCnt);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int status = statusIO;
-  for (int tl = warp; tl < A.nt; tl += NW)
+  for (int tl = warp; tl < A.nt; tl += NWC)
     build_list<E>(dxs, dys, A.K0, A.ox, A.oy, A.cosT[A.t0 + tl], A.sinT[A.t0 + tl], A.bx, A.by, A.ul, A.nHalf,
                   A.Wx, A.Wy, lists + tl * A.Kpad, cnts + tl, lane, status);
   statusIO = status;
+}
+
+
+// ---- union window ------------------------------------------------------------------------------------------
+// The coarse window and every fine window the coarse stage can select lie inside est +- RU.  That union is read
+// ONCE per particle (instead of once per stage): 16-byte streaming loads, two rows / 18 loads in flight per lane,
+// thresholded visited/total > 0.5 <=> 2*visited > total (ScanMatcher_OGBased.py:29-31) and packed with warp ballots
+// into an L2-resident bitmap (word 2t = cells 64t+2l, word 2t+1 = cells 64t+2l+1 of a row).  Each stage then
+// scatters the set bits of its own window through its float64 index maps (:36-37).
+__device__ __forceinline__ void union_window(const MatchParams& P, int p, int (&w)[4]) {
+  const double x = P.estPose[3 * p], y = P.estPose[3 * p + 1];
+  int x0 = (int)floor(ddiv(dsub(dsub(x, P.RU), P.mapX0), P.unit)) - 1;
+  int y0 = (int)floor(ddiv(dsub(dsub(y, P.RU), P.mapY0), P.unit)) - 1;
+  int x1 = (int)ceil(ddiv(dsub(dadd(x, P.RU), P.mapX0), P.unit)) + 2;
+  int y1 = (int)ceil(ddiv(dsub(dadd(y, P.RU), P.mapY0), P.unit)) + 2;
+  x0 = max(x0, 0) & ~1; y0 = max(y0, 0);
+  x1 = min(x1, P.G); y1 = min(y1, P.G);
+  int nc = max(x1 - x0, 0);
+  nc = min((nc + 1) & ~1, P.UWcells);
+  if (x0 + nc > P.pitch) nc = (P.pitch - x0) & ~1;
+  w[0] = y0; w[1] = x0; w[2] = min(max(y1 - y0, 0), P.URows); w[3] = nc;
+}
+
+constexpr int UF4 = 9;     // float4 per lane per row: rows up to 32*9*2 = 576 cells
+
+__device__ __noinline__ void build_union_bitmap(const MatchParams& P, int p, unsigned* U, const int (&w)[4]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int uy0 = w[0], ux0 = w[1], nrows = w[2], nc = w[3];
+  const float4* g = reinterpret_cast<const float4*>(P.grid + (size_t)p * P.G * P.pitch * 2 + ((size_t)uy0 * P.pitch + ux0) * 2);
+  const size_t rowF4 = (size_t)P.pitch / 2;
+  const int nf4 = nc / 2;
+  const int nIter = (nf4 + 31) / 32;
+  if (nrows <= 0 || nf4 <= 0) return;
+  for (int r0 = warp * 2; r0 < nrows; r0 += NWC * 2) {
+    for (int t0 = 0; t0 < nIter; t0 += UF4) {
+      float4 v[2][UF4];
+      // unconditional loads from clamped addresses (so all 18 are in flight together); out-of-range lanes are masked
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4* rowp = g + (size_t)min(r0 + h, nrows - 1) * rowF4;
+#pragma unroll
+        for (int u = 0; u < UF4; ++u) v[h][u] = ld_stream_f4(rowp + min((t0 + u) * 32 + lane, nf4 - 1));
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int u = 0; u < UF4; ++u)
+          if ((t0 + u) * 32 + lane >= nf4) v[h][u] = make_float4(0.f, 1.f, 0.f, 1.f);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        unsigned mine = 0u;
+#pragma unroll
+        for (int u = 0; u < UF4; ++u) {
+          const unsigned we = __ballot_sync(FULL, 2.f * v[h][u].x > v[h][u].y);   // cells 64t + 2*lane
+          const unsigned wo = __ballot_sync(FULL, 2.f * v[h][u].z > v[h][u].w);   // cells 64t + 2*lane + 1
+          if (lane == 2 * u) mine = we;
+          if (lane == 2 * u + 1) mine = wo;
+        }
+        if (r0 + h < nrows && lane < 2 * UF4 && 2 * t0 + lane < P.UW) U[(size_t)(r0 + h) * P.UW + 2 * t0 + lane] = mine;
+      }
+    }
+  }
 }
 
 struct StageOut {
@@ -624,7 +707,8 @@ struct StageOut {
 template <bool FAST, bool DENSE>
 __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, int p, double cx, double cy, double cth,
                           bool sample, double uniform, unsigned char* gslot, BlockScratch& bs, int& status,
-                          StageOut& out, long long* cyc) {
+                          StageOut& out, long long* cyc, const unsigned* U, const int* uwin, int prefetchP,
+                          unsigned* Unext, int* uwinNext) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double ul = S.unitLength;
   const int r = S.r;
@@ -654,63 +738,86 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
   const int Pp = S.Ppitch;
   constexpr bool dense = DENSE;                      // coarse: dense field in shared memory, ungated gathers
 
-  __syncthreads();  // previous users of the arena are done
+  csync();  // previous users of the arena are done
   if (cyc && tid == 0) cyc[0] -= clock64();
 
   // ---- B. clear bitmap, float64 index maps (:36 via :173-176) -- rows of OccupancyGridX are identical
-  for (int i = tid; i < Wy * words; i += NT) bits[i] = 0u;
-  for (int i = tid; i < Wx * WT; i += NT) bitsT[i] = 0u;
+  for (int i = tid; i < Wy * words; i += NTC) bits[i] = 0u;
+  for (int i = tid; i < Wx * WT; i += NTC) bitsT[i] = 0u;
   if (dense)
-    for (int i = tid; i < Wy * Pp; i += NT) Pf[i] = S.B2;
-  for (int j = tid; j < ncols; j += NT) {
+    for (int i = tid; i < Wy * Pp; i += NTC) Pf[i] = S.B2;
+  for (int j = tid; j < ncols; j += NTC) {
     int c = (int)ddiv(dsub(P.gridX[mx0 + j], xr0), ul);
     if (c < 0 || c >= Wx) { status |= SLAM_ST_INDEX_OUT_OF_FIELD; c = min(max(c, 0), Wx - 1); }
     colMap[j] = (short)c;
   }
-  for (int i = tid; i < nrows; i += NT) {
+  for (int i = tid; i < nrows; i += NTC) {
     int c = (int)ddiv(dsub(P.gridY[my0 + i], yr0), ul);
     if (c < 0 || c >= Wy) { status |= SLAM_ST_INDEX_OUT_OF_FIELD; c = min(max(c, 0), Wy - 1); }
     rowMap[i] = (short)c;
   }
-  __syncthreads();
+  csync();
 
-  // ---- C. stream the window: occupied <=> visited/total > 0.5 <=> 2*visited > total (:29-31), scatter (:37)
+  // ---- C. scatter the occupied cells of this stage's window (:29-37) out of the particle's union bitmap, which the
+  //         streaming warp built in the background (bit planes: word 2t = cells 64t+2l, word 2t+1 = cells 64t+2l+1).
   {
-    const float* g = P.grid + (size_t)p * P.G * P.pitch * 2;
-    const int mxa = mx0 & ~1;                         // 16-byte aligned start
-    const int npairs = (mx1 - mxa + 1) >> 1;
-    for (int i = warp; i < nrows; i += NW) {
-      const float4* rowp = (const float4*)(g + ((size_t)(my0 + i) * P.pitch + mxa) * 2);
-      const int fr = (int)rowMap[i];
-      const int rbase = fr * words;
-      const int tw = fr >> 5;
-      const unsigned tb = 1u << (fr & 31);
-      for (int q0 = 0; q0 < npairs; q0 += 8 * 32) {
-        float4 v[8];
+    const int uy0 = uwin[0], ux0 = uwin[1], unr = uwin[2], unc = uwin[3];
+    if (my0 < uy0 || my1 > uy0 + unr || mx0 < ux0 || mx1 > ux0 + unc) {
+      if (nrows > 0 && ncols > 0) status |= SLAM_ST_WINDOW_OUTSIDE_MAP;     // union window was clipped
+    }
+    const int UW = P.UW;
+    const int wlo = ((mx0 - ux0) >> 6) * 2, whi = min((((mx1 - 1 - ux0) >> 6) + 1) * 2, UW);
+    const int nw = max(whi - wlo, 0);
+    const int rlo = max(my0 - uy0, 0), rhi = min(my1 - uy0, unr);
+    const int total = max(rhi - rlo, 0) * nw;
+    // a warp takes 32 bitmap words at a time and spreads their set bits evenly over its lanes: lane j handles the
+    // j-th set bit of the group (owner word by binary search over the popcount prefix, bit by __fns)
+    auto loadw = [&](int base) -> unsigned {
+      const int idx = base + lane;
+      if (idx >= total) return 0u;
+      const int rr = idx / nw;
+      return __ldcg(U + (size_t)(rlo + rr) * UW + wlo + (idx - rr * nw));
+    };
+    unsigned wnext = loadw(warp * 32);
+    for (int base = warp * 32; base < total; base += NWC * 32) {
+      const unsigned wmine = wnext;
+      wnext = loadw(base + NWC * 32);                    // next group's words are in flight while this one is expanded
+      const int cnt = __popc(wmine);
+      int incl = cnt;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          int q = q0 + u * 32 + lane;
-          v[u] = (q < npairs) ? ld_stream_f4(rowp + q) : make_float4(0.f, 1.f, 0.f, 1.f);
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+      }
+      const int tot = __shfl_sync(FULL, incl, 31);
+      const int excl = incl - cnt;
+      for (int j0 = 0; j0 < tot; j0 += 32) {
+        const int j = min(j0 + lane, tot - 1);
+        int L = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+          const int probe = __shfl_sync(FULL, incl, L + step - 1);
+          if (probe <= j) L += step;
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          int q = q0 + u * 32 + lane;
-          int j0 = mxa + 2 * q - mx0;                // window column of the first cell of the pair
-          if (2.f * v[u].x > v[u].y && j0 >= 0 && j0 < ncols) {
-            int c = colMap[j0];
-            atomicOr(&bits[rbase + (c >> 5)], 1u << (c & 31));
-            atomicOr(&bitsT[c * WT + tw], tb);
-          }
-          if (2.f * v[u].z > v[u].w && j0 + 1 >= 0 && j0 + 1 < ncols) {
-            int c = colMap[j0 + 1];
-            atomicOr(&bits[rbase + (c >> 5)], 1u << (c & 31));
-            atomicOr(&bitsT[c * WT + tw], tb);
+        const unsigned wv = __shfl_sync(FULL, wmine, L);
+        const int kth = j - __shfl_sync(FULL, excl, L);
+        if (j0 + lane < tot) {
+          const int bit = __fns(wv, 0, kth + 1);
+          const int id2 = base + L;
+          const int rr = id2 / nw, wi = wlo + (id2 - rr * nw);
+          const int i = uy0 + rlo + rr - my0;                               // window row
+          const int jc = ((wi >> 1) << 6) + (wi & 1) + 2 * bit + ux0 - mx0;   // window column
+          if (jc >= 0 && jc < ncols) {
+            const int fr = (int)rowMap[i];
+            const int c = colMap[jc];
+            atomicOr(&bits[fr * words + (c >> 5)], 1u << (c & 31));
+            atomicOr(&bitsT[c * WT + (fr >> 5)], 1u << (fr & 31));
           }
         }
       }
     }
   }
-  __syncthreads();
+  csync();
   if (cyc && tid == 0) { long long t = clock64(); cyc[0] += t; cyc[1] -= t; }
 
   // ---- D. separable blur in scipy's order, only where the result can differ from the background.
@@ -733,20 +840,28 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
     if (probMin < S.B2) status |= SLAM_ST_INDEX_OUT_OF_FIELD;   // cannot happen (monotone rounding); fail loudly
     if (thr == 0.0) {
       thr = dmul(0.5, probMin);
-      for (int i = tid; i < Wy * Wx; i += NT) {
+      for (int i = tid; i < Wy * Wx; i += NTC) {
         const int yy = i / Wx, xx = i - yy * Wx;
         if ((dil[yy * words + (xx >> 5)] >> (xx & 31)) & 1u) {
           double* q = Pf + (size_t)yy * Pp + xx;
           if (*q > thr) *q = 0.0;
         }
       }
-      __syncthreads();
+      csync();
     }
+  }
+  if (prefetchP >= 0) {     // staggered HBM phase: this CTA reads its next particle's union window here
+    if (cyc && tid == 0) cyc[7] -= clock64();
+    int uw[4];
+    union_window(P, prefetchP, uw);
+    build_union_bitmap(P, prefetchP, Unext, uw);
+    if (tid < 4) uwinNext[tid] = uw[tid];
+    if (cyc && tid == 0) cyc[7] += clock64();
   }
   if (cyc && tid == 0) { long long t = clock64(); cyc[1] += t; cyc[2] -= t; }
   if (P.dbgProb[stageId]) {
     double* d = P.dbgProb[stageId] + (size_t)p * S.Wmax * S.Wmax;
-    for (int i = tid; i < Wy * Wx; i += NT) {
+    for (int i = tid; i < Wy * Wx; i += NTC) {
       const int yy = i / Wx, xx = i - yy * Wx;
       const bool on = dense || ((dil[yy * words + (xx >> 5)] >> (xx & 31)) & 1u);
       d[yy * S.Wmax + xx] = on ? Pf[(size_t)yy * Pp + xx] : S.B2;
@@ -763,7 +878,7 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
     const double start = dsub(cth, P.fovHalf), stop = dadd(cth, P.fovHalf);
     const double step = ddiv(dsub(stop, start), (double)(K - 1));
     int base = 0;
-    for (int k0 = 0; k0 < K; k0 += NT) {     // K <= 512 -> one trip
+    for (int k0 = 0; k0 < K; k0 += NTC) {     // K <= 512 -> one trip
       const int k = k0 + tid;
       bool keep = false;
       double ddx = 0, ddy = 0;
@@ -777,13 +892,13 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
         ddx = dsub(px, cx); ddy = dsub(py, cy);                                          // (px - ox) of :169
       }
       unsigned bal = __ballot_sync(FULL, keep);
-      __syncthreads();
+      csync();
       if (lane == 0) bs.ival[warp] = __popc(bal);
-      __syncthreads();
+      csync();
       int before = base;
       for (int w2 = 0; w2 < warp; ++w2) before += bs.ival[w2];
       int tot = 0;
-      for (int w2 = 0; w2 < NW; ++w2) tot += bs.ival[w2];
+      for (int w2 = 0; w2 < NWC; ++w2) tot += bs.ival[w2];
       if (keep) {
         int pos = before + __popc(bal & ((1u << lane) - 1u));
         dxs[pos] = ddx; dys[pos] = ddy;
@@ -792,7 +907,7 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
     }
     K0 = base;
   }
-  __syncthreads();
+  csync();
 
   if (cyc && tid == 0) cyc[2] += clock64();
   // ---- G. per-theta lists + score volume, TB thetas at a time
@@ -821,17 +936,17 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
     LA.nt = nt; LA.t0 = t0;
     if (S.E == 8) lists_batch<8>(LA, status);
     else lists_batch<16>(LA, status);
-    __syncthreads();
+    csync();
     if (cyc && tid == 0) { long long t = clock64(); cyc[3] += t; cyc[4] -= t; }
     SA.nt = nt; SA.t0 = t0;
     score_batch<FAST, DENSE>(SA, best, bestIdx, sawNan);
-    __syncthreads();
+    csync();
     if (cyc && tid == 0) cyc[4] += clock64();
   }
   if (cyc && tid == 0) cyc[5] -= clock64();
 
   // ---- H. select (:133-141)
-  if (__syncthreads_or(sawNan)) status |= SLAM_ST_NAN_SCORE;
+  if (csync_or(sawNan)) status |= SLAM_ST_NAN_SCORE;
   int chosen;
   {  // first maximum in C order
 #pragma unroll
@@ -841,30 +956,30 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
       if (oi >= 0 && (bestIdx < 0 || ob > best || (ob == best && oi < bestIdx))) { best = ob; bestIdx = oi; }
     }
     if (lane == 0) { bs.dval[warp] = best; bs.ival[warp] = bestIdx; }
-    __syncthreads();
+    csync();
     double b = bs.dval[0];
     int bi = bs.ival[0];
-    for (int w2 = 1; w2 < NW; ++w2) {
+    for (int w2 = 1; w2 < NWC; ++w2) {
       double ob = bs.dval[w2];
       int oi = bs.ival[w2];
       if (oi >= 0 && (bi < 0 || ob > b || (ob == b && oi < bi))) { b = ob; bi = oi; }
     }
     chosen = bi;
-    __syncthreads();
+    csync();
   }
   double conf = 0.0;
   if (S.needScores) {
     const int n = S.nPoses;
-    for (int i = tid; i < n; i += NT) scores[i] = exp(scores[i]);
-    __syncthreads();
+    for (int i = tid; i < n; i += NTC) scores[i] = exp(scores[i]);
+    csync();
     double* leafSum = sbuf<double>(S.oLeaf);
     SmemVal sv;
     sv.a = scores;
-    for (int l = tid; l < S.nLeaves; l += NT) {
+    for (int l = tid; l < S.nLeaves; l += NTC) {
       int2 lf = S.leaves[l];
       leafSum[l] = block_sum(sv, lf.x, lf.y);
     }
-    __syncthreads();
+    csync();
     if (tid == 0) {   // combine the leaves along numpy's recursion tree
       double stack[24];
       int sp = 0;
@@ -875,13 +990,13 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
       }
       bs.bcast[0] = stack[0];
     }
-    __syncthreads();
+    csync();
     conf = bs.bcast[0];
     if (sample) {
       // np.random.choice: p = e / e.sum(); cdf = cumsum(p) (sequential); cdf /= cdf[-1]; searchsorted(u, 'right').
       // Parallel prefix with a certified margin; the exact sequential walk only when u is within the rounding
       // envelope of a CDF step (probability ~1e-10 per call).
-      const int chunk = (n + NT - 1) / NT;
+      const int chunk = (n + NTC - 1) / NTC;
       const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
       double part = 0.0;
       for (int i = lo; i < hi; ++i) part += ddiv(scores[i], conf);
@@ -893,15 +1008,15 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
         if (lane >= d) incl += v;
       }
       if (lane == 31) bs.dval[warp] = incl;
-      __syncthreads();
+      csync();
       double wbase = 0.0, total = 0.0;
-      for (int w2 = 0; w2 < NW; ++w2) {
+      for (int w2 = 0; w2 < NWC; ++w2) {
         if (w2 < warp) wbase += bs.dval[w2];
         total += bs.dval[w2];
       }
       const double before = wbase + incl - part;
       if (tid == 0) { bs.ibcast[0] = -1; bs.ibcast[1] = 0; }
-      __syncthreads();
+      csync();
       const double tol = 1e-10;
       if (hi > lo && before / total <= uniform && ((before + part) / total > uniform || hi == n)) {
         double c = before, prev = before;
@@ -918,10 +1033,10 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
           if (old != -1 || amb) bs.ibcast[1] = 1;
         }
       }
-      __syncthreads();
+      csync();
       int idx = bs.ibcast[0];
       bool exact = P.forceExactCdf || idx < 0 || bs.ibcast[1];
-      __syncthreads();
+      csync();
       if (exact) {
         if (tid == 0) {
           double c = 0.0;
@@ -935,7 +1050,7 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
           }
           bs.ibcast[0] = min(found, n - 1);
         }
-        __syncthreads();
+        csync();
         idx = bs.ibcast[0];
       }
       chosen = idx;
@@ -954,23 +1069,63 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
 
 __global__ void __launch_bounds__(NT, 1) match_kernel(const __grid_constant__ MatchParams P) {
   __shared__ BlockScratch bs;
+  __shared__ int s_uwin[2][4];
   unsigned char* gslot = P.scratch + (size_t)blockIdx.x * P.slotBytes;
+  unsigned* Ubuf[2];
+  Ubuf[0] = reinterpret_cast<unsigned*>(gslot + P.gU);
+  Ubuf[1] = Ubuf[0] + (size_t)P.URows * P.UW;
   long long* cyc = P.dbgCycles ? P.dbgCycles + (size_t)blockIdx.x * 16 : nullptr;
-  for (int p = blockIdx.x; p < P.N; p += gridDim.x) {
+  // The union window of particle k+1 is read while particle k is being processed, at a point of the phase sequence
+  // that depends on the CTA index: CTAs run the same phases in lock step, so reading at the same point would
+  // alternate between a saturated and an idle HBM.  Staggering spreads the stream over the whole step.
+  const int point = blockIdx.x % 5;
+  int k = 0;
+  {   // prologue: first particle of this CTA
+    const int p0 = blockIdx.x;
+    if (p0 < P.N) {
+      int uw[4];
+      union_window(P, p0, uw);
+      build_union_bitmap(P, p0, Ubuf[0], uw);
+      if (threadIdx.x < 4) s_uwin[0][threadIdx.x] = uw[threadIdx.x];
+    }
+  }
+  for (int p = blockIdx.x; p < P.N; p += gridDim.x, ++k) {
     const double x = P.estPose[3 * p], y = P.estPose[3 * p + 1], th = P.estPose[3 * p + 2];
     int status = 0;
     StageOut c, f;
     const bool sample = P.uniforms != nullptr;
     const double u = sample ? P.uniforms[p] : 0.0;
     long long* cyc2 = cyc ? cyc + 8 : nullptr;
+    const int pn = (p + (int)gridDim.x < P.N) ? p + (int)gridDim.x : -1;
+    unsigned* Ucur = Ubuf[k & 1];
+    unsigned* Unext = Ubuf[(k + 1) & 1];
+    int* wcur = s_uwin[k & 1];
+    int* wnext = s_uwin[(k + 1) & 1];
+    csync();                                  // bitmap / window descriptor of this particle are complete
+    auto prefetch_here = [&](int pt) {
+      if (pn >= 0 && point == pt) {
+        if (cyc && threadIdx.x == 0) cyc[6] -= clock64();
+        int uw[4];
+        union_window(P, pn, uw);
+        build_union_bitmap(P, pn, Unext, uw);
+        if (threadIdx.x < 4) wnext[threadIdx.x] = uw[threadIdx.x];
+        if (cyc && threadIdx.x == 0) cyc[6] += clock64();
+      }
+    };
+    prefetch_here(0);
+    const int preC = (pn >= 0 && point == 1) ? pn : -1;     // after the coarse blur
+    const int preF = (pn >= 0 && point == 3) ? pn : -1;     // after the fine blur
     if (P.fast) {      // everything but the sparse fine field lives in shared memory
-      run_stage<true, true>(P, P.st[0], 0, p, x, y, th, sample, u, gslot, bs, status, c, cyc);
-      run_stage<true, false>(P, P.st[1], 1, p, c.x, c.y, c.th, false, 0.0, gslot, bs, status, f, cyc2);
+      run_stage<true, true>(P, P.st[0], 0, p, x, y, th, sample, u, gslot, bs, status, c, cyc, Ucur, wcur, preC, Unext, wnext);
+      prefetch_here(2);
+      run_stage<true, false>(P, P.st[1], 1, p, c.x, c.y, c.th, false, 0.0, gslot, bs, status, f, cyc2, Ucur, wcur, preF, Unext, wnext);
     } else {           // large windows: bitmaps / fields / scores in the global slot
-      run_stage<false, false>(P, P.st[0], 0, p, x, y, th, sample, u, gslot, bs, status, c, cyc);
-      run_stage<false, false>(P, P.st[1], 1, p, c.x, c.y, c.th, false, 0.0, gslot, bs, status, f, cyc2);
+      run_stage<false, false>(P, P.st[0], 0, p, x, y, th, sample, u, gslot, bs, status, c, cyc, Ucur, wcur, preC, Unext, wnext);
+      prefetch_here(2);
+      run_stage<false, false>(P, P.st[1], 1, p, c.x, c.y, c.th, false, 0.0, gslot, bs, status, f, cyc2, Ucur, wcur, preF, Unext, wnext);
     }
-    status = __syncthreads_or(status);
+    prefetch_here(4);
+    status = csync_or(status);
     if (threadIdx.x == 0) {
       P.outPose[3 * p] = f.x; P.outPose[3 * p + 1] = f.y; P.outPose[3 * p + 2] = f.th;
       P.outConf[p] = c.conf;
@@ -1211,6 +1366,19 @@ extern "C" int slam_matcher_create(const slam_geometry* g, const slam_matcher_de
     return rc;
   }
   P.fast = fast ? 1 : 0;
+  // background stream: union window geometry, 2-stage ring after everything else, two union bitmaps in the slot
+  {
+    const double coarseReach = d->coarse.nHalf * d->coarse.unitLength;
+    P.RU = d->windowRadius + coarseReach + 2.0 * g->unit;
+    P.UWcells = (((int)(2.0 * P.RU / g->unit) + 8) + 63) / 64 * 64;     // multiple of 64 cells (2 bitmap words)
+    P.UWcells = std::min(P.UWcells, (g->pitch / 2) * 2);
+    P.UW = 2 * ((P.UWcells + 63) / 64);
+    P.URows = std::min((int)(2.0 * P.RU / g->unit) + 8, g->G);
+    P.ringRows = 0;
+    P.oRing = 0;
+    P.gU = align_up(slot, 256);
+    slot = P.gU + 2 * (size_t)P.URows * P.UW * 4;     // double buffered: next particle's bitmap is built early
+  }
   m->smemBytes = smemNeed;
   P.slotBytes = align_up(slot, 256);
   m->numCtas = sms;
