@@ -422,8 +422,14 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
       const int i = i0 + sub;
       unsigned v = 0u;
       if (i < Wy && w < words) {
+        if (i - r >= 0 && i + r < Wy) {                  // interior: no reflection, unit-stride rows
+          const unsigned* q = bits + (i - r) * words + w;
 #pragma unroll
-        for (int d = -r; d <= r; ++d) v |= bits[reflect_idx(i + d, Wy) * words + w];
+          for (int d = 0; d <= 2 * r; ++d) v |= q[d * words];
+        } else {
+#pragma unroll
+          for (int d = -r; d <= r; ++d) v |= bits[reflect_idx(i + d, Wy) * words + w];
+        }
       }
       unsigned lo = __shfl_up_sync(FULL, v, 1, seg), hi = __shfl_down_sync(FULL, v, 1, seg);
       if (w == 0) lo = 0u;

@@ -1,0 +1,86 @@
+"""CPU (gloo, world_size 2): the host-side logic of the multi-GPU path -- shard bounds, the resample transfer plan
+and its execution with point-to-point sends -- without any GPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _load_plan_functions():
+    """distributed.py imports the CUDA package; the planning helpers are pure Python, so load them from source."""
+    import ast
+    src = open(os.path.join(ROOT, "slam-2d-lidar-scan_b200", "distributed.py")).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("shard_bounds", "plan_resample_transfers")]
+    ns = {}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "distributed_plan", "exec"), ns)
+    return ns["shard_bounds"], ns["plan_resample_transfers"]
+
+
+def test_shard_bounds_and_plan_are_consistent():
+    shard_bounds, plan = _load_plan_functions()
+    assert shard_bounds(8, 2) == [(0, 4), (4, 8)]
+    with pytest.raises(ValueError):
+        shard_bounds(9, 2)
+    rng = np.random.default_rng(0)
+    for world, n in ((2, 8), (4, 16), (8, 64)):
+        nl = n // world
+        idx = rng.integers(0, n, n)
+        plans = plan(idx, nl, world)
+        got = {}
+        for r, pl in enumerate(plans):
+            for d, s in pl["local"]:
+                got[r * nl + d] = r * nl + s
+            for srcRank, d, tag in pl["recvs"]:
+                # the matching send exists on the source rank, same destination slot
+                sends = [x for x in plans[srcRank]["sends"] if x[0] == r and x[2] == tag]
+                assert len(sends) == 1
+                got[r * nl + d] = srcRank * nl + sends[0][1]
+        assert [got[i] for i in range(n)] == [int(v) for v in idx]
+        # deterministic pairing: per (src, dst) pair the sends and recvs appear in the same order
+        for a in range(world):
+            for b in range(world):
+                s_tags = [t for (dst, _, t) in plans[a]["sends"] if dst == b]
+                r_tags = [t for (src, _, t) in plans[b]["recvs"] if src == a]
+                assert s_tags == r_tags
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shard_bounds, plan = _load_plan_functions()
+    n, nl = 8, 4
+    lo, hi = shard_bounds(n, world)[rank]
+    # replicated decision: every rank holds all weights after the all-gather and draws the same uniforms
+    mine = torch.arange(lo, hi, dtype=torch.float64).view(-1, 1) * torch.ones(1, 4, dtype=torch.float64)
+    allw = torch.zeros(n, 4, dtype=torch.float64)
+    dist.all_gather_into_tensor(allw, mine)
+    assert torch.equal(allw[:, 0], torch.arange(n, dtype=torch.float64))
+    idx = np.random.RandomState(5).randint(0, n, n)            # same on both ranks
+    pl = plan(idx, nl, world)[rank]
+    grids = torch.stack([torch.full((3,), float(lo + i)) for i in range(nl)])     # "lattice" i holds its global id
+    new = torch.full_like(grids, -1.0)
+    for d, s in pl["local"]:
+        new[d] = grids[s]
+    ops = [dist.P2POp(dist.isend, grids[s], dstRank) for dstRank, s, _ in pl["sends"]]
+    ops += [dist.P2POp(dist.irecv, new[d], srcRank) for srcRank, d, _ in pl["recvs"]]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    ok = all(float(new[i, 0]) == float(idx[lo + i]) for i in range(nl))
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_resample_transfers_over_gloo_world2():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]
