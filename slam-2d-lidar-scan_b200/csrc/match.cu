@@ -23,7 +23,7 @@
 
 namespace slam {
 
-constexpr int NT = 512;          // threads per CTA
+constexpr int NT = 512;          // threads per CTA (768 x 85 registers was measured: no gain, spills)
 constexpr int NW = NT / 32;      // warps per CTA
 constexpr int NWC = NW;          // compute warps (all of them; a dedicated streaming warp could not keep up)
 constexpr int NTC = NWC * 32;    // compute threads
@@ -665,6 +665,7 @@ __device__ __forceinline__ void union_window(const MatchParams& P, int p, int (&
 }
 
 constexpr int UF4 = 9;     // float4 per lane per row: rows up to 32*9*2 = 576 cells
+constexpr int URW = NT > 512 ? 1 : 2;   // rows per warp iteration (URW*UF4 16-byte loads in flight per lane)
 
 __device__ __noinline__ void build_union_bitmap(const MatchParams& P, int p, unsigned* U, const int (&w)[4]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -674,23 +675,23 @@ __device__ __noinline__ void build_union_bitmap(const MatchParams& P, int p, uns
   const int nf4 = nc / 2;
   const int nIter = (nf4 + 31) / 32;
   if (nrows <= 0 || nf4 <= 0) return;
-  for (int r0 = warp * 2; r0 < nrows; r0 += NWC * 2) {
+  for (int r0 = warp * URW; r0 < nrows; r0 += NWC * URW) {
     for (int t0 = 0; t0 < nIter; t0 += UF4) {
-      float4 v[2][UF4];
+      float4 v[URW][UF4];
       // unconditional loads from clamped addresses (so all 18 are in flight together); out-of-range lanes are masked
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < URW; ++h) {
         const float4* rowp = g + (size_t)min(r0 + h, nrows - 1) * rowF4;
 #pragma unroll
         for (int u = 0; u < UF4; ++u) v[h][u] = ld_stream_f4(rowp + min((t0 + u) * 32 + lane, nf4 - 1));
       }
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
+      for (int h = 0; h < URW; ++h)
 #pragma unroll
         for (int u = 0; u < UF4; ++u)
           if ((t0 + u) * 32 + lane >= nf4) v[h][u] = make_float4(0.f, 1.f, 0.f, 1.f);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < URW; ++h) {
         unsigned mine = 0u;
 #pragma unroll
         for (int u = 0; u < UF4; ++u) {

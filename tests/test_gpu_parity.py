@@ -255,3 +255,86 @@ def test_window_outside_map_raises_like_an_unexpandable_map(S, frames):
     og.updateOccupancyGrid(reading(frames[0]))
     with pytest.raises(IndexError):
         sm.matchScan(reading(frames[1]), 0.0, None, 2)
+
+
+def test_360_beam_full_circle_scan_matches_oracle(S):
+    """BASELINE config 5 flavour: 360 beams over 2*pi (numSpokes 360, spokesStartIdx 270, 512-key sorts), synthetic
+    scene, 3 particles; poses / indices exact, maps exact."""
+    from slam_2d_lidar_scan_b200 import synthetic
+    init = {"x": 0.0, "y": 0.0}
+    ogp = [50, 50, init, 0.1, 2 * np.pi, 10, 360, 0.5]
+    smp = [1.0, 0.3, 2, 0.1, 0.25, 0.3, 0.15, 2]
+    scene = synthetic.make_scene(seed=3, steps=6, K=360, fov=2 * np.pi, unit=0.1)
+
+    def run(cls):
+        np.random.seed(21)
+        pf = cls(3, ogp, smp)
+        out = []
+        for fr in scene["warm"]:
+            for p in pf.particles:
+                p.og.updateOccupancyGrid(fr)
+        for count, fr in enumerate(scene["frames"][:6], start=1):
+            pf.updateParticles(fr, count)
+            pf.weightUnbalanced()
+            out.append(pf.poses() if hasattr(pf, "poses") else _poses(pf))
+        return pf, out
+    pf, got = run(S.ParticleFilter)
+    ref, want = run(O.ParticleFilter)
+    assert pf.geom.numSpokes == 360 and pf.geom.spokesStartIdx == 270
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    np.testing.assert_allclose(pf.weights.cpu().numpy(), [p.weight for p in ref.particles], rtol=1e-9, atol=0)
+    for i in range(3):
+        assert np.array_equal(pf.particles[i].og.occupancyGridTotal, ref.particles[i].og.occupancyGridTotal)
+        assert np.array_equal(pf.particles[i].og.occupancyGridVisited, ref.particles[i].og.occupancyGridVisited)
+
+
+def test_large_batch_properties_c3(S):
+    """BASELINE config 3 size (1024 particles, 1001^2 lattices): size-independent properties instead of the oracle.
+    (1) identical particles + argmax (no sampling) -> identical results in every slot, equal to the 1-particle run;
+    (2) counts stay integer valued and only ever grow; (3) weights normalise to 1."""
+    from slam_2d_lidar_scan_b200 import synthetic
+    spec = synthetic.config("c3")
+    scene = synthetic.make_scene(seed=0, steps=4, K=180, fov=np.pi, unit=0.05)
+    outs = []
+    for n in (1024, 1):
+        np.random.seed(9)
+        pf = S.ParticleFilter(n, spec["og"], spec["sm"])
+        og = S.OccupancyGrid(*pf.geom.args, _geometry=pf.geom)
+        for fr in scene["warm"]:
+            og.updateOccupancyGrid(fr)
+        pf.grids.copy_(og.device_grid.unsqueeze(0).expand_as(pf.grids))
+        before = pf.grids.clone() if n == 1 else None
+        # deterministic variant of the step: argmax in the coarse stage (uniforms = None)
+        K = pf.geom.numSamplesPerRev
+        for count, fr in enumerate(scene["frames"][:3], start=1):
+            rec = pf._prepare(fr, count, n, pf._prevRaw[0], pf._prevRawHeading[0])
+            pf._stage_d.copy_(pf._stage_h)
+            if count > 1:
+                eng, st = pf.engine, torch.cuda.current_stream().cuda_stream
+                nat = S._native
+                nat.check(nat.lib.slam_propose_poses(n, pf.prevMatched.data_ptr(), rec["rawTheta"], rec["prevRawTheta"], 0, 0.0,
+                                                     pf.prevHeading.data_ptr(), pf.hasHeading.data_ptr(), pf._est.data_ptr(),
+                                                     pf._phi.data_ptr(), pf._hasPhi.data_ptr(), pf.status.data_ptr(), st))
+                n2 = eng.nOffC ** 2
+                eng.match(pf.grids, n, pf._stage_d[:K], pf._est, pf._stage_d[K + n:K + n + n2], None, None, pf._matched,
+                          pf._conf, pf._idx, pf.status)
+                nat.check(nat.lib.slam_finish_step(n, pf._matched.data_ptr(), pf._conf.data_ptr(), pf.prevMatched.data_ptr(),
+                                                   pf.prevHeading.data_ptr(), pf.hasHeading.data_ptr(), pf.weights.data_ptr(), st))
+                from slam_2d_lidar_scan_b200.engine import update_grids
+                update_grids(pf.geom, pf.grids, n, pf._stage_d[:K], pf._matched, pf.status)
+            else:
+                pf._launch(0, n, rec, pf._stage_d)
+            pf._prevRaw, pf._prevRawHeading = [fr] * n, [rec["newRawHeading"]] * n
+        assert int(pf.status.max().item()) == 0
+        pf.weightUnbalanced()
+        outs.append((pf.prevMatched.cpu().numpy(), pf._idx.cpu().numpy(), pf.weights.cpu().numpy(), pf.grids[0].cpu().numpy()))
+        if n == 1024:
+            assert np.all(outs[0][0] == outs[0][0][0]) and np.all(outs[0][1] == outs[0][1][0])
+            assert torch.equal(pf.grids[1023], pf.grids[0]) and torch.equal(pf.grids[511], pf.grids[0])
+            assert abs(outs[0][2].sum() - 1.0) < 1e-12
+        else:
+            g = pf.grids[0]
+            assert torch.equal(g, g.round()) and bool((g >= before[0]).all())
+    assert np.array_equal(outs[0][0][0], outs[1][0][0]) and np.array_equal(outs[0][1][0], outs[1][1][0])
+    assert np.array_equal(outs[0][3], outs[1][3])
