@@ -145,6 +145,18 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic(workload, nLocal):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one match_kernel launch from the committed `ncu --set full`
+    capture of this same command (profiles/r1_match_traffic.json), or None if no capture matches the workload."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_match_traffic.json")))
+    except (OSError, ValueError):
+        return None
+    if t.get("workload") == workload and t.get("particles") == nLocal:
+        return t.get("dram_bytes_per_launch")
+    return None
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_b200(args):
     import torch
@@ -272,7 +284,7 @@ def run_b200(args):
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "slam::match_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args.workload, nLocal),
                          "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_launch": nLocal * bmatch, "ms_per_launch": ms_match,
                          "share_of_step": ms_match / (ms_dev / K)},
@@ -320,7 +332,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c5"])

@@ -43,25 +43,51 @@ __global__ void finish_kernel(int N, const double* matched, const double* conf, 
   weights[p] = dmul(weights[p], conf[p]);
 }
 
-// normalizeWeights (:43-48) + weightUnbalanced trigger (:32-37): sequential float64, one thread.
-__global__ void normalize_kernel(int N, double* w, double* out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// normalizeWeights (:43-48) + weightUnbalanced trigger (:32-37).  The two accumulations are sequential float64 by
+// contract (one thread adds, in index order); the independent per-element work (loads, divisions, squares) is done
+// by the whole block through a shared-memory tile so the adding thread never waits on memory or on a divide.
+constexpr int NORM_T = 1024;
+__global__ void __launch_bounds__(NORM_T) normalize_kernel(int N, double* w, double* out) {
+  __shared__ double tile[NORM_T];
+  __shared__ double s_sum;
+  const int tid = threadIdx.x;
   double s = 0.0;
-  for (int i = 0; i < N; ++i) s = dadd(s, w[i]);
+  for (int i0 = 0; i0 < N; i0 += NORM_T) {
+    if (i0 + tid < N) tile[tid] = w[i0 + tid];
+    __syncthreads();
+    if (tid == 0) {
+      const int n = min(NORM_T, N - i0);
+      for (int i = 0; i < n; ++i) s = dadd(s, tile[i]);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) s_sum = s;
+  __syncthreads();
+  s = s_sum;
   const double n = (double)N;
   const double invN = ddiv(1.0, n);
   double var = 0.0;
-  for (int i = 0; i < N; ++i) {
-    const double wi = ddiv(w[i], s);
-    w[i] = wi;
-    const double d = dsub(wi, invN);
-    var = dadd(var, dmul(d, d));
+  for (int i0 = 0; i0 < N; i0 += NORM_T) {
+    if (i0 + tid < N) {
+      const double wi = ddiv(w[i0 + tid], s);
+      w[i0 + tid] = wi;
+      const double d = dsub(wi, invN);
+      tile[tid] = dmul(d, d);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int m = min(NORM_T, N - i0);
+      for (int i = 0; i < m; ++i) var = dadd(var, tile[i]);
+    }
+    __syncthreads();
   }
-  // ((N-1)/N)**2 + (N - 1.000000000000001) * (1/N)**2
-  const double a = ddiv(n - 1.0, n);
-  const double thr = dadd(dmul(a, a), dmul(dsub(n, 1.000000000000001), dmul(invN, invN)));
-  out[0] = var;
-  out[1] = var > thr ? 1.0 : 0.0;
+  if (tid == 0) {
+    // ((N-1)/N)**2 + (N - 1.000000000000001) * (1/N)**2
+    const double a = ddiv(n - 1.0, n);
+    const double thr = dadd(dmul(a, a), dmul(dsub(n, 1.000000000000001), dmul(invN, invN)));
+    out[0] = var;
+    out[1] = var > thr ? 1.0 : 0.0;
+  }
 }
 
 // legacy RandomState.choice: sequential cumsum, normalise by the last element, searchsorted side='right'
@@ -132,7 +158,7 @@ extern "C" int slam_finish_step(int32_t N, const double* d_matched, const double
 
 extern "C" int slam_normalize_weights(int32_t N, double* d_weights, double* d_out, void* stream) {
   if (N <= 0 || !d_weights || !d_out) return fail(SLAM_E_BADARG, "slam_normalize_weights: bad argument");
-  normalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(N, d_weights, d_out);
+  normalize_kernel<<<1, NORM_T, 0, (cudaStream_t)stream>>>(N, d_weights, d_out);
   SLAM_CUDA(cudaGetLastError());
   return 0;
 }

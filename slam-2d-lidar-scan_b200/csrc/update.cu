@@ -47,14 +47,16 @@ __global__ void update_prep_kernel(UpdParams P) {
   if (lane == 0) {
     // spokesOffsetIdxByTheta = int(rint(theta / (2*pi) * numSpokes))  (:131)
     const int off = (int)rint(dmul(ddiv(th, 6.283185307179586), (double)P.numSpokes));
-    P.prep[warp] = make_int4(sx, sy, off, pure ? UPD_PURE : 0);
+    int shift = (P.start + off) % P.numSpokes;          // beam i looks at sector (shift + i) % numSpokes (:134)
+    if (shift < 0) shift += P.numSpokes;
+    P.prep[warp] = make_int4(sx, sy, shift, pure ? UPD_PURE : 0);
     if (!pure) P.slow[1 + atomicAdd(&P.slow[0], 1)] = warp;
   }
 }
 
-__device__ __forceinline__ int beam_of(int sector, int start, int off, int numSpokes) {
-  int b = (sector - start - off) % numSpokes;    // inverse of spokeIdx = (start + off + i) % numSpokes (:134)
-  return b < 0 ? b + numSpokes : b;
+__device__ __forceinline__ int beam_of(int sector, int shift, int numSpokes) {
+  const int b = sector - shift;                  // inverse of spokeIdx = (start + off + i) % numSpokes (:134)
+  return b < 0 ? b + numSpokes : b;              // sector, shift in [0, numSpokes)
 }
 
 // Fast path: thread owns local cells; loops over a chunk of particles with the table entry in registers.
@@ -74,23 +76,46 @@ __global__ void __launch_bounds__(256) update_fast_kernel(UpdParams P) {
   const double r = P.radius[cell];
   const size_t gstride = (size_t)P.G * P.pitch;
   int bad = 0;
-  for (int q = 0; q < np; ++q) {
-    const int4 pr = s_prep[q];
-    if (!(pr.w & UPD_PURE)) continue;
-    const int beam = beam_of(sec, P.start, pr.z, P.numSpokes);
-    if (beam >= P.K) continue;
-    const double rm = s_ranges[beam];
-    const double lo = dsub(rm, P.wallHalf), hi = dadd(rm, P.wallHalf);
-    const bool empty = rm < P.maxRange && r < lo;
-    const bool hit = r > lo && r < hi;
-    if (!(empty || hit)) continue;
-    const int jx = pr.x + lx, jy = pr.y + ly;
-    if (jx < 0 || jy < 0 || jx >= P.G || jy >= P.G) { bad = 1; continue; }
-    float2* c = (float2*)P.grid + (size_t)(p0 + q) * gstride + (size_t)jy * P.pitch + jx;
-    float2 v = *c;
-    if (empty) v.y += 1.f;
-    if (hit) { v.x += 2.f; v.y += 2.f; }
-    *c = v;
+  // particles of the chunk in groups of 8: all reads of a group are issued before its writes (distinct particles
+  // own distinct lattices, so the read-modify-writes are independent)
+  for (int q0 = 0; q0 < np; q0 += 8) {
+    float2* ptr[8];
+    float2 val[8];
+    unsigned char flag[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      flag[j] = 0;
+      ptr[j] = nullptr;
+      const int q = q0 + j;
+      if (q < np) {
+        const int4 pr = s_prep[q];
+        const int beam = beam_of(sec, pr.z, P.numSpokes);
+        if ((pr.w & UPD_PURE) && beam < P.K) {
+          const double rm = s_ranges[beam];
+          const double lo = dsub(rm, P.wallHalf), hi = dadd(rm, P.wallHalf);
+          const unsigned char f = ((rm < P.maxRange && r < lo) ? 1 : 0) | ((r > lo && r < hi) ? 2 : 0);
+          if (f) {
+            const int jx = pr.x + lx, jy = pr.y + ly;
+            if (jx < 0 || jy < 0 || jx >= P.G || jy >= P.G) bad = 1;
+            else {
+              flag[j] = f;
+              ptr[j] = (float2*)P.grid + (size_t)(p0 + q) * gstride + (size_t)jy * P.pitch + jx;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (flag[j]) val[j] = *ptr[j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (flag[j]) {
+        float2 v = val[j];
+        if (flag[j] & 1) v.y += 1.f;
+        if (flag[j] & 2) { v.x += 2.f; v.y += 2.f; }
+        *ptr[j] = v;
+      }
   }
   if (bad) {
     // conservative: flag every particle of the chunk that was written out of bounds is not tracked per particle
@@ -138,7 +163,7 @@ __device__ void update_general_one(const UpdParams& P, int p, int* mx, int* my) 
       const int lx = cx - 1 + dx;
       if (lx < 0 || lx >= P.L || mx[lx] != jx) continue;
       const int lc = ly * P.L + lx;
-      const int beam = beam_of(P.sector[lc], P.start, pr.z, P.numSpokes);
+      const int beam = beam_of(P.sector[lc], pr.z, P.numSpokes);
       if (beam >= P.K) continue;
       const double rm = P.ranges[beam], r = P.radius[lc];
       const double lo = dsub(rm, P.wallHalf), hi = dadd(rm, P.wallHalf);
