@@ -58,8 +58,8 @@ struct StageDev {
   // ---- plan
   int Wmax, Wmap, words, WT, Ppitch, TB, Kpad, E;   // words includes >= 1 always-zero spare word per row
   int bitsInSmem, PInSmem, scoresInSmem, needScores;
-  int oBits, oBitsT, oDil, oVw, oRow, oCol, oP, oLists, oCnt, oScores, oDx, oDy, oLeaf;
-  size_t gBits, gBitsT, gDil, gP, gScores;  // byte offsets inside a CTA's global scratch slot
+  int oBits, oBitsT, oDil, oVw, oRow, oCol, oTiles, oP, oLists, oCnt, oScores, oDx, oDy, oLeaf;
+  size_t gBits, gBitsT, gDil, gTiles, gP, gScores;  // byte offsets inside a CTA's global scratch slot
 };
 
 struct MatchParams {
@@ -395,6 +395,8 @@ __device__ __forceinline__ double block_min(double v, BlockScratch& bs) {
 }
 
 
+constexpr int TPI = 2;   // active tiles a warp blurs at a time (independent dependency chains interleave)
+
 // ---- separable blur (phase D) templated on the radius so every tap loop unrolls and its loads pipeline.
 // RT == 0: generic run-time radius.  Returns (through refs) the running minimum and the number of active cells.
 template <int RT, bool FAST, bool DENSE>
@@ -407,10 +409,13 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
   unsigned* dil = buf<FAST, unsigned>(S.oDil, gslot, S.gDil);
   double* Pf = DENSE ? sbuf<double>(S.oP) : reinterpret_cast<double*>(gslot + S.gP);
   double* VwAll = sbuf<double>(S.oVw);
+  unsigned* tiles = buf<FAST, unsigned>(S.oTiles, gslot, S.gTiles);   // ids of the active tiles (order irrelevant)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = RT ? RT : S.r;
   const int words = S.words, WT = S.WT;
   if (tid <= 2 * r) s_w[tid] = S.w[tid];
+  if (tid == 0) { counter[0] = 0; counter[1] = 0; }
+  csync();
   int myActive = 0;
   // D1. activity bitmap: cell (i, j) is active iff an occupied cell lies within +-r rows and +-r columns
   //     (reflected taps always fall inside that span, so plain dilation is exact).
@@ -443,6 +448,16 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
         dil[i * words + w] = dl;
         myActive += __popc(dl);
       }
+      {   // warp-aggregated append of the active tiles of this step
+        const bool act = (i < Wy && w < words) && dl != 0u;
+        const unsigned am = __ballot_sync(FULL, act);
+        if (am) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&counter[0], __popc(am));
+          base = __shfl_sync(FULL, base, 0);
+          if (act) tiles[base + __popc(am & ((1u << lane) - 1u))] = (unsigned)(i * words + w);
+        }
+      }
     }
   } else {
     for (int t = tid; t < Wy * words; t += NTC) {
@@ -460,9 +475,9 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
       if (valid < 32) dl &= valid <= 0 ? 0u : ((1u << valid) - 1u);
       dil[t] = dl;
       myActive += __popc(dl);
+      if (dl != 0u) tiles[atomicAdd(&counter[0], 1)] = (unsigned)t;
     }
   }
-  if (tid == 0) *counter = 0;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) myActive += __shfl_xor_sync(FULL, myActive, d);
   if (lane == 0) s_active[warp] = myActive;
@@ -475,45 +490,36 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
   const bool anyInactive = nActive < Wx * Wy;
   const double thr = anyInactive ? dmul(0.5, S.B2) : 1.0;   // field values are <= 0: 1.0 never clamps
   const double* __restrict__ lut = S.lutV;
-  // D2. active tiles (32 columns x 1 row), two per warp at a time (independent dependency chains interleave).
+  // D2. active tiles (32 columns x 1 row) from the compacted list, TPI per warp at a time.
   //     First pass (axis 0) depends only on the 2r+1 occupancy bits of a column:
   //       out = x[c]*w[r]; out += (x[c+j] + x[c-j])*w[j+r], j = -r..-1, with x in {log(missProb), 0}.
   double mn = 0.0;
   const int nTiles = Wy * words;
-  double* Vw = VwAll + warp * 128;
+  double* Vw = VwAll + warp * (TPI * 64);
   const unsigned patMask = (2u << (2 * r)) - 1u;
+  const int nList = counter[0];
   for (;;) {
-    int tb = 0;
-    if (lane == 0) tb = atomicAdd(counter, 32);
-    tb = __shfl_sync(FULL, tb, 0);
-    if (tb >= nTiles) break;
-    const int tmine = tb + lane;
-    const unsigned wmine = tmine < nTiles ? dil[tmine] : 0u;
-    unsigned am = __ballot_sync(FULL, wmine != 0u);
-    while (am) {
-      int tt[2];
-      unsigned dls[2];
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&counter[1], TPI);
+    base = __shfl_sync(FULL, base, 0);
+    if (base >= nList) break;
+    {
+      int tt[TPI];
+      unsigned dls[TPI];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (am) {
-          const int b = __ffs(am) - 1;
-          am &= am - 1;
-          tt[u] = tb + b;
-          dls[u] = __shfl_sync(FULL, wmine, b);
-        } else {
-          tt[u] = -1;
-          dls[u] = 0u;
-        }
+      for (int u = 0; u < TPI; ++u) {
+        tt[u] = base + u < nList ? (int)tiles[base + u] : -1;
+        dls[u] = tt[u] >= 0 ? dil[tt[u]] : 0u;
       }
-      int ti[2], tw[2];
+      int ti[TPI], tw[TPI];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < TPI; ++u) {
         ti[u] = tt[u] < 0 ? 0 : tt[u] / words;
         tw[u] = tt[u] < 0 ? 0 : tt[u] - ti[u] * words;
       }
       // virtual columns 32w-r .. 32w+31+r: lane handles vc0 = 32w-r+lane and (lane < 2r) vc1 = vc0+32
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < TPI; ++u) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int i = ti[u];
@@ -537,7 +543,7 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
       __syncwarp();
       // second pass (axis 1) for the active cells of the tiles
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < TPI; ++u) {
         if ((dls[u] >> lane) & 1u) {
           const double* c = Vw + u * 64 + lane + r;       // virtual column of cell 32w+lane
           double val = dmul(c[0], s_w[r]);
@@ -733,7 +739,6 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
   mx1 = min(mx1, mx0 + S.Wmap); my1 = min(my1, my0 + S.Wmap);
   const int ncols = max(mx1 - mx0, 0), nrows = max(my1 - my0, 0);
   const int words = S.words;
-  const int nStrips = (Wx + 31) >> 5;
 
   unsigned* bits = buf<FAST, unsigned>(S.oBits, gslot, S.gBits);
   unsigned* bitsT = buf<FAST, unsigned>(S.oBitsT, gslot, S.gBitsT);    // [col][WT] transposed
@@ -1307,13 +1312,14 @@ static int plan_stage(slam_matcher* m, const slam_geometry* g, const slam_stage_
     S.oDil = S.bitsInSmem ? take(bitsBytes) : 0;      // activity bitmap lives through the correlation
     S.oDx = take(dxyBytes);
     S.oDy = take(dxyBytes);
-    S.oVw = take((size_t)NW * 128 * 8);
+    S.oVw = take((size_t)NW * TPI * 64 * 8);
     const size_t common = off;
     // window / blur-phase buffers
     S.oBits = S.bitsInSmem ? take(bitsBytes) : 0;
     S.oBitsT = S.bitsInSmem ? take(bitsTBytes) : 0;
     S.oRow = take(mapBytes);
     S.oCol = take(mapBytes);
+    S.oTiles = S.bitsInSmem ? take(bitsBytes) : 0;     // active-tile ids (one 32-bit id per bitmap word at most)
     const size_t blurEnd = off;
     // correlate-phase buffers alias the blur-phase ones
     off = common;
@@ -1328,6 +1334,7 @@ static int plan_stage(slam_matcher* m, const slam_geometry* g, const slam_stage_
       S.gBits = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsBytes, 256);
       S.gBitsT = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsTBytes, 256);
       S.gDil = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsBytes, 256);
+      S.gTiles = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsBytes, 256);
       S.gP = g0; g0 += S.PInSmem ? 0 : align_up(PBytes, 256);
       S.gScores = g0; g0 += (S.needScores && !S.scoresInSmem) ? align_up(scoreBytes, 256) : 0;
       slotBytes = g0;

@@ -338,3 +338,26 @@ def test_large_batch_properties_c3(S):
             assert torch.equal(g, g.round()) and bool((g >= before[0]).all())
     assert np.array_equal(outs[0][0][0], outs[1][0][0]) and np.array_equal(outs[0][1][0], outs[1][1][0])
     assert np.array_equal(outs[0][3], outs[1][3])
+
+
+def test_dataset_drivers_reproduce_the_reference_loop(S, frames):
+    """drivers.run_scanmatch / run_mapping are the reference's main() loops (F3): same golden poses and maps."""
+    from slam_2d_lidar_scan_b200 import drivers
+    data = {fr["key"]: reading(fr) for fr in frames}
+    init = {"x": frames[0]["x"], "y": frames[0]["y"]}
+    g = load_golden("det_c3.npz")
+    og = S.OccupancyGrid(*OG_C3(init))
+    sm = S.ScanMatcher(og, *SM_C3)
+    poses, confs = drivers.run_scanmatch(data, og, sm, maxFrames=30)
+    assert np.array_equal(poses, g["poses"])
+    np.testing.assert_allclose(confs, g["confs"], rtol=CONF_RTOL, atol=0)
+    g2 = load_golden("update_c3.npz")
+    og2 = S.OccupancyGrid(*OG_C3(init))
+    drivers.run_mapping(data, og2, maxFrames=12)
+    v, t = dense_counts(int(g2["G"][0]), g2["cells"], g2["visited"], g2["total"])
+    assert np.array_equal(og2.occupancyGridVisited, v) and np.array_equal(og2.occupancyGridTotal, t)
+    np.random.seed(0)
+    pf = S.ParticleFilter(3, [50, 50, init, 0.05, np.pi, 10, 180, 0.25], list(SM_C3))
+    best, fired, b = drivers.run_fastslam(pf, data, maxFrames=22)
+    g3 = load_golden("pf_c3.npz")
+    assert np.array_equal(pf.poses(), g3["poses"][21]) and not fired.any()
