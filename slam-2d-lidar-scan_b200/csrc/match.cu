@@ -23,7 +23,7 @@
 
 namespace slam {
 
-constexpr int NT = 512;          // threads per CTA (768 x 85 registers was measured: no gain, spills)
+constexpr int NT = 512;          // threads per CTA (768 x 85 and 1024 x 64 registers were measured: no gain)
 constexpr int NW = NT / 32;      // warps per CTA
 constexpr int NWC = NW;          // compute warps (all of them; a dedicated streaming warp could not keep up)
 constexpr int NTC = NWC * 32;    // compute threads

@@ -62,11 +62,25 @@ __device__ __forceinline__ int beam_of(int sector, int shift, int numSpokes) {
 // Fast path: thread owns local cells; loops over a chunk of particles with the table entry in registers.
 constexpr int UPD_CHUNK = 32;
 __global__ void __launch_bounds__(256) update_fast_kernel(UpdParams P) {
-  extern __shared__ double s_ranges[];
+  // per-sector interval tables of this scan: a cell of beam b is seen-empty iff r < loE[b] and hit iff lo[b] < r < hi[b]
+  // (:138-143); sectors outside the fan get intervals that are never satisfied, so no beam < K test is needed
+  extern __shared__ double s_tab[];
+  double* s_loE = s_tab;
+  double* s_lo = s_tab + P.numSpokes;
+  double* s_hi = s_tab + 2 * P.numSpokes;
   __shared__ int4 s_prep[UPD_CHUNK];
   const int p0 = blockIdx.y * UPD_CHUNK;
   const int np = min(UPD_CHUNK, P.N - p0);
-  for (int k = threadIdx.x; k < P.K; k += blockDim.x) s_ranges[k] = P.ranges[k];
+  for (int k = threadIdx.x; k < P.numSpokes; k += blockDim.x) {
+    double loE = -INFINITY, lo = INFINITY, hi = -INFINITY;
+    if (k < P.K) {
+      const double rm = P.ranges[k];
+      lo = dsub(rm, P.wallHalf);
+      hi = dadd(rm, P.wallHalf);
+      if (rm < P.maxRange) loE = lo;
+    }
+    s_loE[k] = loE; s_lo[k] = lo; s_hi[k] = hi;
+  }
   if (threadIdx.x < np) s_prep[threadIdx.x] = P.prep[p0 + threadIdx.x];
   __syncthreads();
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
@@ -90,10 +104,8 @@ __global__ void __launch_bounds__(256) update_fast_kernel(UpdParams P) {
       if (q < np) {
         const int4 pr = s_prep[q];
         const int beam = beam_of(sec, pr.z, P.numSpokes);
-        if ((pr.w & UPD_PURE) && beam < P.K) {
-          const double rm = s_ranges[beam];
-          const double lo = dsub(rm, P.wallHalf), hi = dadd(rm, P.wallHalf);
-          const unsigned char f = ((rm < P.maxRange && r < lo) ? 1 : 0) | ((r > lo && r < hi) ? 2 : 0);
+        if (pr.w & UPD_PURE) {
+          const unsigned char f = (r < s_loE[beam] ? 1 : 0) | ((r > s_lo[beam] && r < s_hi[beam]) ? 2 : 0);
           if (f) {
             const int jx = pr.x + lx, jy = pr.y + ly;
             if (jx < 0 || jy < 0 || jx >= P.G || jy >= P.G) bad = 1;
@@ -237,7 +249,7 @@ extern "C" int slam_update_grid(const slam_geometry* g, float* d_grid, int32_t N
   SLAM_CUDA(cudaGetLastError());
   {
     dim3 grid((g->L * g->L + 255) / 256, (N + UPD_CHUNK - 1) / UPD_CHUNK);
-    update_fast_kernel<<<grid, 256, g->K * sizeof(double), st>>>(P);
+    update_fast_kernel<<<grid, 256, 3 * g->numSpokes * sizeof(double), st>>>(P);
     SLAM_CUDA(cudaGetLastError());
   }
   {
