@@ -100,10 +100,12 @@ def cpu_baseline(workload, steps=6, procs=None):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, enabled=True):
+        self.index, self.rows, self.proc, self.enabled = index, [], None, enabled
 
     def __enter__(self):
+        if not self.enabled:      # only rank 0 polls nvidia-smi: N pollers would steal host cores from the N ranks
+            return self
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -214,7 +216,7 @@ def run_b200(args):
     pf._prevRaw, pf._prevRawHeading = [prevRaw] * nLocal, [prevHead] * nLocal
     sync_all()
     launches0 = None
-    with ClockSampler(local) as clk1:
+    with ClockSampler(local, rank == 0) as clk1:
         for i in range(W + K):
             if i == W:
                 sync_all()
@@ -244,7 +246,7 @@ def run_b200(args):
         api_step()
     sync_all()
     h0, d0 = pf.h2dBytes, pf.d2hBytes
-    with ClockSampler(local) as clk2:
+    with ClockSampler(local, rank == 0) as clk2:
         t0 = time.perf_counter()
         for _ in range(K):
             api_step()
