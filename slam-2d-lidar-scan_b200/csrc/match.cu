@@ -1,18 +1,20 @@
 // Fused multi-resolution correlative scan matcher for a batch of particles (sm_100a).
 //
 // One persistent CTA per SM walks over particles; for each particle it runs the coarse and the fine stage of
-// ScanMatcher.matchScan (Utils/ScanMatcher_OGBased.py:47-79) entirely on chip, except for the fine likelihood
-// field which lives in a per-CTA global scratch slot (L2-resident):
+// ScanMatcher.matchScan (Utils/ScanMatcher_OGBased.py:47-79) with every intermediate on chip, except the sparse
+// fine likelihood field and the occupancy bitmap of the particle's window, which live in a per-CTA L2-resident slot:
 //
-//   window   visited/total window -> occupancy bits, scattered through the float64 index maps       (:20-37)
-//   blur     separable symmetric correlation in scipy's exact operation order, exploiting that the
-//            input takes two values {log(missProb), 0}; background tiles are skipped (their value is a
-//            host-computed constant produced by the same operation order)                            (:41-42)
-//   clamp    probMin = global min; prob[prob > 0.5*probMin] = 0                                       (:43-44)
-//   points   beam end points, compaction of beams < maxRange                                          (:81-89)
-//   lists    per theta: rotate, truncate to indices, sort + unique (lexicographic (x, y))             (:116-121)
-//   scores   per (theta, dy, dx): gather + numpy-pairwise sum + priors                                (:125-132)
-//   select   first-max argmax, or exp / pairwise sum / CDF inversion of one host uniform; confidence  (:133-141)
+//   union    one streaming read of the union of the coarse and all possible fine windows -> packed occupancy bits
+//            (visited/total > 0.5 <=> 2*visited > total), issued one particle ahead and staggered across CTAs  (:29-31)
+//   scatter  per stage: set bits -> float64 index maps -> row-major + transposed shared-memory bitmaps       (:32-37)
+//   blur     separable symmetric correlation in scipy's exact operation order, exploiting that the input takes two
+//            values {log(missProb), 0}: first pass = table lookup on a column's 2r+1 bits, second pass only on
+//            active 32-cell tiles; background = host-computed constant from the same operation order          (:41-42)
+//   clamp    probMin = global min (= the background constant whenever one inactive cell exists); applied in the blur (:43-44)
+//   points   beam end points, compaction of beams < maxRange                                                  (:81-89)
+//   lists    per theta: rotate, truncate to indices, warp bitonic sort + unique (lexicographic (x, y))        (:116-121)
+//   scores   per (theta, dy, 2 adjacent dx): gathers + numpy-pairwise sum + priors                            (:125-132)
+//   select   first-max argmax, or exp / pairwise sum / CDF inversion of one host uniform; confidence          (:133-141)
 //
 // Numerics: IEEE float64, no FMA contraction, numpy's pairwise-summation order and scipy's pair-add/multiply/
 // accumulate order are reproduced literally so that the score volume is bit-identical to the oracle's.
