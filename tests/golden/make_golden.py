@@ -11,6 +11,8 @@ Writes (committed, small):
     tests/golden/pf_c3.npz             seeded FastSLAM (np.random.seed(0)), 3 particles, c3 geometry, 22 frames
     tests/golden/update_c3.npz         mapping with known poses (OccupancyGrid.updateOccupancyGrid only)
     tests/golden/resample.npz          ParticleFilter.resample / weightUnbalanced known answers
+    tests/golden/csail_gfs_head.json   first 20 readings of DataSet/PreprocessedData/csail_gfs (361 beams; input only)
+    tests/golden/det_csail.npz         deterministic driver on the CSAIL readings, c3-like geometry, 20 frames
 
 Nothing here is product code; the reference is only imported, never copied.
 """
@@ -41,10 +43,10 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def load_frames():
-    with open(os.path.join(REF, "DataSet/PreprocessedData/intel_gfs")) as f:
+def load_frames(name="intel_gfs", n=N_FRAMES):
+    with open(os.path.join(REF, "DataSet/PreprocessedData", name)) as f:
         data = json.load(f)["map"]
-    keys = sorted(data.keys())[:N_FRAMES]
+    keys = sorted(data.keys())[:n]
     return [dict(key=k, x=data[k]["x"], y=data[k]["y"], theta=data[k]["theta"], range=data[k]["range"]) for k in keys]
 
 
@@ -200,6 +202,14 @@ def main():
     np.savez_compressed(os.path.join(HERE, "pf_c3.npz"), **run_fastslam(frames, ogp, list(sm_c3), 3, 22, seed=0))
 
     np.savez_compressed(os.path.join(HERE, "update_c3.npz"), **run_update_only(frames, og_c3, 12))
+
+    # MIT CSAIL log: 361 beams (numSpokes 722), poses near x = 576 m (different float noise in the index maps)
+    cs = load_frames("csail_gfs", 20)
+    with open(os.path.join(HERE, "csail_gfs_head.json"), "w") as f:
+        json.dump({"source": "DataSet/PreprocessedData/csail_gfs, first 20 readings (sorted keys)", "frames": cs}, f)
+    cinit = {"x": cs[0]["x"], "y": cs[0]["y"]}
+    og_cs = (50, 50, cinit, 0.05, np.pi, 361, 10, 0.25)
+    np.savez_compressed(os.path.join(HERE, "det_csail.npz"), **run_deterministic(cs, og_cs, sm_c3, 20, {3, 12}))
     np.savez_compressed(os.path.join(HERE, "resample.npz"), **run_resample())
     for fn in sorted(os.listdir(HERE)):
         p = os.path.join(HERE, fn)

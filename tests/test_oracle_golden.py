@@ -117,3 +117,22 @@ def test_weights_trigger_and_resample_known_answers():
         for slot in (0, n - 1):
             w = np.full(n, 1e-30); w[slot] = 1.0
             assert O.unbalanced(O.normalize([float(x) for x in w]))[0] == bool(g["degenerate_%d_%d" % (n, slot)][0])
+
+
+def test_csail_361_beam_driver_matches_reference():
+    """MIT CSAIL readings: 361 beams (numSpokes 722), poses ~576 m from the origin (index-map float noise)."""
+    import json, os
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "csail_gfs_head.json")) as f:
+        cs = json.load(f)["frames"]
+    g = load_golden("det_csail.npz")
+    init = {"x": cs[0]["x"], "y": cs[0]["y"]}
+    grid, poses, confs, traces = drive_deterministic(cs, (50, 50, init, 0.05, np.pi, 361, 10, 0.25), SM_C3, 20, (3, 12))
+    assert grid.geom.numSpokes == 722 and grid.geom.K == 361
+    assert np.array_equal(poses, g["poses"]) and np.array_equal(confs, g["confs"])
+    v, t = dense_counts(int(g["G"][0]), g["cells"], g["visited"], g["total"])
+    assert np.array_equal(grid.occupancyGridVisited, v) and np.array_equal(grid.occupancyGridTotal, t)
+    for c in (3, 12):
+        for k, stage in enumerate(("coarse", "fine")):
+            assert np.array_equal(traces[c][k]["vol"], g["c%d_%s_vol" % (c, stage)])
+            assert np.array_equal(sha(traces[c][k]["prob"]), g["c%d_%s_prob_sha" % (c, stage)])
