@@ -231,7 +231,7 @@ def run_b200(args):
     ms_dev = e0.elapsed_time(e1)
     matchMs = [a.elapsed_time(b) for a, b in pf.matchEvents]
     pf.matchEvents = None
-    st = int(pf.status.max().item())
+    st = int(pf.status.max().item())      # sticky OR-ed status words: any non-zero word has a bit set
     if st:
         raise RuntimeError("status bits %d set during the timed run" % st)
 

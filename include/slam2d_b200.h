@@ -128,7 +128,7 @@ typedef struct {
  *  d_outPose   [N][3] double            fine-stage matched pose
  *  d_outConf   [N] double               coarse confidence = sum(exp(convTotal))
  *  d_outIdx    [N][6] int32             (itheta, iy, ix) coarse then fine
- *  d_status    [N] int32                SLAM_ST_* bits
+ *  d_status    [N] int32                SLAM_ST_* bits, OR-ed into the existing words (never cleared here)
  */
 int slam_match_scan(slam_matcher* m, const float* d_grid, int32_t N, const double* d_ranges,
                     const double* d_estPose, const double* d_rv, const double* d_tw,
@@ -170,6 +170,10 @@ int slam_finish_step(int32_t N, const double* d_matched, const double* d_conf, d
 /* normalizeWeights + weightUnbalanced (FastSlam.py:30-48) with the reference's sequential float64 order.
  * d_out[0] = variance, d_out[1] = 1.0 if the trigger fires else 0.0. */
 int slam_normalize_weights(int32_t N, double* d_weights, double* d_out, void* stream);
+
+/* d_out[0] = bitwise OR of the N per-particle status words.  Status words are sticky: every kernel ORs its bits
+ * in, nothing clears them but the caller (numpy would have raised at the first one: ScanMatcher_OGBased.py:125-138). */
+int slam_status_reduce(int32_t N, const int32_t* d_status, int32_t* d_out, void* stream);
 
 /* np.random.choice(arange(N), N, p=w) given the N uniforms it would draw (legacy RandomState):
  * cdf = cumsum(w) sequential; cdf /= cdf[-1]; idx = searchsorted(cdf, u, side='right').

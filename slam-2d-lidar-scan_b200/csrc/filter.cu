@@ -90,6 +90,20 @@ __global__ void __launch_bounds__(NORM_T) normalize_kernel(int N, double* w, dou
   }
 }
 
+// bitwise OR of the per-particle status words (one block)
+__global__ void status_or_kernel(int N, const int* status, int* out) {
+  __shared__ int s_or;
+  if (threadIdx.x == 0) s_or = 0;
+  __syncthreads();
+  int v = 0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) v |= status[i];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, d);
+  if ((threadIdx.x & 31) == 0 && v) atomicOr(&s_or, v);
+  __syncthreads();
+  if (threadIdx.x == 0) out[0] = s_or;
+}
+
 // legacy RandomState.choice: sequential cumsum, normalise by the last element, searchsorted side='right'
 __global__ void cdf_kernel(int N, const double* w, double* cdf) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -159,6 +173,13 @@ extern "C" int slam_finish_step(int32_t N, const double* d_matched, const double
 extern "C" int slam_normalize_weights(int32_t N, double* d_weights, double* d_out, void* stream) {
   if (N <= 0 || !d_weights || !d_out) return fail(SLAM_E_BADARG, "slam_normalize_weights: bad argument");
   normalize_kernel<<<1, NORM_T, 0, (cudaStream_t)stream>>>(N, d_weights, d_out);
+  SLAM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int slam_status_reduce(int32_t N, const int32_t* d_status, int32_t* d_out, void* stream) {
+  if (N <= 0 || !d_status || !d_out) return fail(SLAM_E_BADARG, "slam_status_reduce: bad argument");
+  status_or_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(N, d_status, d_out);
   SLAM_CUDA(cudaGetLastError());
   return 0;
 }

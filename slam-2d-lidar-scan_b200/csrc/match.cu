@@ -18,6 +18,8 @@
 //
 // Numerics: IEEE float64, no FMA contraction, numpy's pairwise-summation order and scipy's pair-add/multiply/
 // accumulate order are reproduced literally so that the score volume is bit-identical to the oracle's.
+#include <cuda.h>   // CUtensorMap (types only; the encoder is resolved through the runtime, no libcuda link)
+
 #include <algorithm>
 #include <vector>
 
@@ -25,11 +27,13 @@
 
 namespace slam {
 
-constexpr int NT = 512;          // threads per CTA (768 x 85 and 1024 x 64 registers were measured: no gain)
-constexpr int NW = NT / 32;      // warps per CTA
-constexpr int NWC = NW;          // compute warps (all of them; a dedicated streaming warp could not keep up)
+constexpr int NT = 480;          // compute threads per CTA: 15 warps + the stream warp = 16 warps x 128 registers (4 per scheduler)
+constexpr int NW = NT / 32;      // compute warps per CTA
+constexpr int NWC = NW;          // compute warps
 constexpr int NTC = NWC * 32;    // compute threads
+constexpr int NT_ALL = NTC + 32; // + one stream warp: TMA producer / occupancy-bit packer of the union window
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int RING_STAGES = 4;   // TMA ring depth (stages of ringRows window rows each)
 
 // barrier over the compute warps (named barrier 1)
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory"); }
@@ -86,7 +90,8 @@ struct MatchParams {
   int UWcells;           // max columns of a union row segment (even)
   int UW;                // bitmap words per union row = 2*ceil(UWcells/64) (even/odd bit planes per 64 cells)
   int URows;             // max union rows
-  int ringRows, oRing;   // rows per ring stage, shared-memory offset of the 2-stage ring
+  int ringRows, oRing;   // window rows per TMA ring stage, shared-memory offset of the RING_STAGES-stage ring
+  int boxCells, nBoxes;  // TMA box = boxCells cells x ringRows rows; nBoxes boxes side by side cover UWcells
   size_t gU;             // offset of the two union bitmaps inside a CTA's global slot
 };
 
@@ -103,6 +108,38 @@ __device__ __forceinline__ double lds_f64(unsigned a) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
   return v;
+}
+
+
+// ---- mbarrier / TMA primitives (PTX; SASS: SYNCS.*, UTMALDG)
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\t"
+      "bra W_%=;\n"
+      "D_%=:\n\t}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+// one box of the lattice tensor (cells as 64-bit elements; x, row, particle) -> shared memory, completion on `bar`;
+// out-of-range elements arrive as zero (visited = total = 0 -> not occupied); streamed through L2 (evict first)
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(c0),
+      "r"(c1), "r"(c2), "l"(0x12F0000000000000ull)
+      : "memory");
 }
 
 // Buffers of the FAST plan are carved out of the dynamic shared-memory array; deriving them from the array itself
@@ -397,6 +434,17 @@ __device__ __forceinline__ double block_min(double v, BlockScratch& bs) {
 }
 
 
+// bitwise OR over the compute warps (status words)
+__device__ __forceinline__ int block_or(int v, BlockScratch& bs) {
+  v = __reduce_or_sync(FULL, v);
+  csync();
+  if ((threadIdx.x & 31) == 0) bs.ival[threadIdx.x >> 5] = v;
+  csync();
+  int r = 0;
+  for (int i = 0; i < NWC; ++i) r |= bs.ival[i];
+  return r;
+}
+
 constexpr int TPI = 2;   // active tiles a warp blurs at a time (independent dependency chains interleave)
 
 // ---- separable blur (phase D) templated on the radius so every tap loop unrolls and its loads pipeline.
@@ -672,45 +720,87 @@ __device__ __forceinline__ void union_window(const MatchParams& P, int p, int (&
   w[0] = y0; w[1] = x0; w[2] = min(max(y1 - y0, 0), P.URows); w[3] = nc;
 }
 
-constexpr int UF4 = 9;     // float4 per lane per row: rows up to 32*9*2 = 576 cells
-constexpr int URW = NT > 512 ? 1 : 2;   // rows per warp iteration (URW*UF4 16-byte loads in flight per lane)
+// mbarriers of the stream pipeline (static shared memory)
+struct StreamShared {
+  unsigned long long ringFull[RING_STAGES];   // TMA complete_tx: a ring stage has landed
+  unsigned long long uFull[2], uEmpty[2];     // union bitmap b is complete / may be overwritten
+};
 
-__device__ __noinline__ void build_union_bitmap(const MatchParams& P, int p, unsigned* U, const int (&w)[4]) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int uy0 = w[0], ux0 = w[1], nrows = w[2], nc = w[3];
-  const float4* g = reinterpret_cast<const float4*>(P.grid + (size_t)p * P.G * P.pitch * 2 + ((size_t)uy0 * P.pitch + ux0) * 2);
-  const size_t rowF4 = (size_t)P.pitch / 2;
-  const int nf4 = nc / 2;
-  const int nIter = (nf4 + 31) / 32;
-  if (nrows <= 0 || nf4 <= 0) return;
-  for (int r0 = warp * URW; r0 < nrows; r0 += NWC * URW) {
-    for (int t0 = 0; t0 < nIter; t0 += UF4) {
-      float4 v[URW][UF4];
-      // unconditional loads from clamped addresses (so all 18 are in flight together); out-of-range lanes are masked
-#pragma unroll
-      for (int h = 0; h < URW; ++h) {
-        const float4* rowp = g + (size_t)min(r0 + h, nrows - 1) * rowF4;
-#pragma unroll
-        for (int u = 0; u < UF4; ++u) v[h][u] = ld_stream_f4(rowp + min((t0 + u) * 32 + lane, nf4 - 1));
+// ---- stream warp.  For every particle of this CTA it stages the union window through a shared-memory ring with
+// TMA tensor loads (cp.async.bulk.tensor, one elected lane; RING_STAGES stages of ringRows rows in flight, no
+// registers tied up) and packs visited/total > 0.5 into the particle's union bitmap while the compute warps are
+// still busy with the previous particle.  Out-of-lattice cells arrive as zeros (not occupied).
+__device__ __noinline__ void stream_role(const MatchParams& P, const CUtensorMap* tmap, StreamShared& sh, int (*s_uwin)[4]) {
+  const int lane = threadIdx.x & 31;
+  unsigned char* gslot = P.scratch + (size_t)blockIdx.x * P.slotBytes;
+  unsigned* Ubuf0 = reinterpret_cast<unsigned*>(gslot + P.gU);
+  const unsigned ring = (smem_u32(sbuf<unsigned char>(0)) + (unsigned)P.oRing + 127u) & ~127u;
+  const int BY = P.ringRows, BX = P.boxCells, nB = P.nBoxes, UW = P.UW;
+  const unsigned boxBytes = (unsigned)(BY * BX * 8), stageBytes = boxBytes * nB;
+  const int tPerBox = BX / 64;
+  const int nMine = (P.N - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // producer cursor (warp-uniform): particle kP, chunk cP of nChP, window wP
+  int kP = 0, cP = 0, nChP = -1, wP[4] = {0, 0, 0, 0};
+  unsigned issued = 0, consumed = 0;
+  auto top_up = [&]() {
+    while (issued - consumed < (unsigned)RING_STAGES && kP < nMine) {
+      const int pP = (int)blockIdx.x + kP * (int)gridDim.x;
+      if (nChP < 0) {
+        union_window(P, pP, wP);
+        nChP = (wP[2] + BY - 1) / BY;
+        cP = 0;
       }
-#pragma unroll
-      for (int h = 0; h < URW; ++h)
-#pragma unroll
-        for (int u = 0; u < UF4; ++u)
-          if ((t0 + u) * 32 + lane >= nf4) v[h][u] = make_float4(0.f, 1.f, 0.f, 1.f);
-#pragma unroll
-      for (int h = 0; h < URW; ++h) {
-        unsigned mine = 0u;
-#pragma unroll
-        for (int u = 0; u < UF4; ++u) {
-          const unsigned we = __ballot_sync(FULL, 2.f * v[h][u].x > v[h][u].y);   // cells 64t + 2*lane
-          const unsigned wo = __ballot_sync(FULL, 2.f * v[h][u].z > v[h][u].w);   // cells 64t + 2*lane + 1
-          if (lane == 2 * u) mine = we;
-          if (lane == 2 * u + 1) mine = wo;
-        }
-        if (r0 + h < nrows && lane < 2 * UF4 && 2 * t0 + lane < P.UW) U[(size_t)(r0 + h) * P.UW + 2 * t0 + lane] = mine;
+      if (cP >= nChP) { ++kP; nChP = -1; continue; }
+      const unsigned st = issued % RING_STAGES;
+      if (lane == 0) {
+        const unsigned bar = smem_u32(&sh.ringFull[st]);
+        mbar_expect_tx(bar, stageBytes);
+        for (int j = 0; j < nB; ++j)
+          tma_load_3d(ring + st * stageBytes + j * boxBytes, tmap, bar, wP[1] + j * BX, wP[0] + cP * BY, pP);
       }
+      ++issued; ++cP;
     }
+  };
+  for (int k = 0; k < nMine; ++k) {
+    const int p = (int)blockIdx.x + k * (int)gridDim.x, b = k & 1;
+    int w[4];
+    union_window(P, p, w);
+    const int nCh = (w[2] + BY - 1) / BY;
+    unsigned* U = Ubuf0 + (size_t)b * P.URows * UW;
+    top_up();                                                     // loads of this (and the next) particle in flight
+    mbar_wait(smem_u32(&sh.uEmpty[b]), (unsigned)(((k >> 1) & 1) ^ 1));   // compute is done with bitmap b
+    if (lane < 4) s_uwin[b][lane] = w[lane];
+    for (int c = 0; c < nCh; ++c) {
+      const unsigned st = consumed % RING_STAGES;
+      mbar_wait(smem_u32(&sh.ringFull[st]), (consumed / RING_STAGES) & 1u);
+      const unsigned stage = ring + st * stageBytes;
+      for (int r = 0; r < BY; ++r) {
+        const int row = c * BY + r;
+        if (row >= w[2]) break;
+        unsigned mine = 0u;
+        int t = 0;
+        for (int j = 0; j < nB; ++j) {
+          const unsigned rowS = stage + (unsigned)(((j * BY + r) * BX + 2 * lane) * 8);
+          for (int tt = 0; tt < tPerBox; ++tt, ++t) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(rowS + 512u * tt));
+            const unsigned we = __ballot_sync(FULL, 2.f * v.x > v.y);   // cells 64t + 2*lane      (:29-31)
+            const unsigned wo = __ballot_sync(FULL, 2.f * v.z > v.w);   // cells 64t + 2*lane + 1
+            if (lane == ((2 * t) & 31)) mine = we;
+            if (lane == ((2 * t + 1) & 31)) mine = wo;
+            if (((2 * t + 1) & 31) == 31 || (j == nB - 1 && tt == tPerBox - 1)) {
+              const int idx = ((2 * t + 1) & ~31) + lane;
+              if (idx <= 2 * t + 1 && idx < UW) U[(size_t)row * UW + idx] = mine;
+              mine = 0u;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      ++consumed;
+      top_up();                                                   // refill the stage just drained
+    }
+    mbar_arrive(smem_u32(&sh.uFull[b]));                          // all 32 lanes: their bitmap words are published
   }
 }
 
@@ -722,8 +812,7 @@ struct StageOut {
 template <bool FAST, bool DENSE>
 __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, int p, double cx, double cy, double cth,
                           bool sample, double uniform, unsigned char* gslot, BlockScratch& bs, int& status,
-                          StageOut& out, long long* cyc, const unsigned* U, const int* uwin, int prefetchP,
-                          unsigned* Unext, int* uwinNext) {
+                          StageOut& out, long long* cyc, const unsigned* U, const int* uwin, unsigned uEmptyBar) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double ul = S.unitLength;
   const int r = S.r;
@@ -832,6 +921,7 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
     }
   }
   csync();
+  if (uEmptyBar && tid == 0) mbar_arrive(uEmptyBar);   // last reader of the union bitmap: the stream warp may reuse it
   if (cyc && tid == 0) { long long t = clock64(); cyc[0] += t; cyc[1] -= t; }
 
   // ---- D. separable blur in scipy's order, only where the result can differ from the background.
@@ -863,14 +953,6 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
       }
       csync();
     }
-  }
-  if (prefetchP >= 0) {     // staggered HBM phase: this CTA reads its next particle's union window here
-    if (cyc && tid == 0) cyc[7] -= clock64();
-    int uw[4];
-    union_window(P, prefetchP, uw);
-    build_union_bitmap(P, prefetchP, Unext, uw);
-    if (tid < 4) uwinNext[tid] = uw[tid];
-    if (cyc && tid == 0) cyc[7] += clock64();
   }
   if (cyc && tid == 0) { long long t = clock64(); cyc[1] += t; cyc[2] -= t; }
   if (P.dbgProb[stageId]) {
@@ -1081,28 +1163,28 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
   if (cyc && tid == 0) cyc[5] += clock64();
 }
 
-__global__ void __launch_bounds__(NT, 1) match_kernel(const __grid_constant__ MatchParams P) {
+__global__ void __launch_bounds__(NT_ALL, 1) match_kernel(const __grid_constant__ MatchParams P,
+                                                           const __grid_constant__ CUtensorMap tmap) {
   __shared__ BlockScratch bs;
   __shared__ int s_uwin[2][4];
+  __shared__ __align__(8) StreamShared ss;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RING_STAGES; ++i) mbar_init(smem_u32(&ss.ringFull[i]), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&ss.uFull[i]), 32); mbar_init(smem_u32(&ss.uEmpty[i]), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // warp NWC: union-window stream (TMA producer + bit packer), runs up to one particle ahead of the compute warps
+  if (threadIdx.x >= NTC) {
+    stream_role(P, &tmap, ss, s_uwin);
+    return;
+  }
   unsigned char* gslot = P.scratch + (size_t)blockIdx.x * P.slotBytes;
   unsigned* Ubuf[2];
   Ubuf[0] = reinterpret_cast<unsigned*>(gslot + P.gU);
   Ubuf[1] = Ubuf[0] + (size_t)P.URows * P.UW;
   long long* cyc = P.dbgCycles ? P.dbgCycles + (size_t)blockIdx.x * 16 : nullptr;
-  // The union window of particle k+1 is read while particle k is being processed, at a point of the phase sequence
-  // that depends on the CTA index: CTAs run the same phases in lock step, so reading at the same point would
-  // alternate between a saturated and an idle HBM.  Staggering spreads the stream over the whole step.
-  const int point = blockIdx.x % 5;
   int k = 0;
-  {   // prologue: first particle of this CTA
-    const int p0 = blockIdx.x;
-    if (p0 < P.N) {
-      int uw[4];
-      union_window(P, p0, uw);
-      build_union_bitmap(P, p0, Ubuf[0], uw);
-      if (threadIdx.x < 4) s_uwin[0][threadIdx.x] = uw[threadIdx.x];
-    }
-  }
   for (int p = blockIdx.x; p < P.N; p += gridDim.x, ++k) {
     const double x = P.estPose[3 * p], y = P.estPose[3 * p + 1], th = P.estPose[3 * p + 2];
     int status = 0;
@@ -1110,42 +1192,26 @@ __global__ void __launch_bounds__(NT, 1) match_kernel(const __grid_constant__ Ma
     const bool sample = P.uniforms != nullptr;
     const double u = sample ? P.uniforms[p] : 0.0;
     long long* cyc2 = cyc ? cyc + 8 : nullptr;
-    const int pn = (p + (int)gridDim.x < P.N) ? p + (int)gridDim.x : -1;
-    unsigned* Ucur = Ubuf[k & 1];
-    unsigned* Unext = Ubuf[(k + 1) & 1];
-    int* wcur = s_uwin[k & 1];
-    int* wnext = s_uwin[(k + 1) & 1];
-    csync();                                  // bitmap / window descriptor of this particle are complete
-    auto prefetch_here = [&](int pt) {
-      if (pn >= 0 && point == pt) {
-        if (cyc && threadIdx.x == 0) cyc[6] -= clock64();
-        int uw[4];
-        union_window(P, pn, uw);
-        build_union_bitmap(P, pn, Unext, uw);
-        if (threadIdx.x < 4) wnext[threadIdx.x] = uw[threadIdx.x];
-        if (cyc && threadIdx.x == 0) cyc[6] += clock64();
-      }
-    };
-    prefetch_here(0);
-    const int preC = (pn >= 0 && point == 1) ? pn : -1;     // after the coarse blur
-    const int preF = (pn >= 0 && point == 3) ? pn : -1;     // after the fine blur
+    const unsigned* Ucur = Ubuf[k & 1];
+    const int* wcur = s_uwin[k & 1];
+    const unsigned uEmpty = smem_u32(&ss.uEmpty[k & 1]);
+    if (cyc && threadIdx.x == 0) cyc[6] -= clock64();
+    mbar_wait(smem_u32(&ss.uFull[k & 1]), (unsigned)((k >> 1) & 1));   // this particle's union bitmap is complete
+    if (cyc && threadIdx.x == 0) cyc[6] += clock64();
     if (P.fast) {      // everything but the sparse fine field lives in shared memory
-      run_stage<true, true>(P, P.st[0], 0, p, x, y, th, sample, u, gslot, bs, status, c, cyc, Ucur, wcur, preC, Unext, wnext);
-      prefetch_here(2);
-      run_stage<true, false>(P, P.st[1], 1, p, c.x, c.y, c.th, false, 0.0, gslot, bs, status, f, cyc2, Ucur, wcur, preF, Unext, wnext);
+      run_stage<true, true>(P, P.st[0], 0, p, x, y, th, sample, u, gslot, bs, status, c, cyc, Ucur, wcur, 0u);
+      run_stage<true, false>(P, P.st[1], 1, p, c.x, c.y, c.th, false, 0.0, gslot, bs, status, f, cyc2, Ucur, wcur, uEmpty);
     } else {           // large windows: bitmaps / fields / scores in the global slot
-      run_stage<false, false>(P, P.st[0], 0, p, x, y, th, sample, u, gslot, bs, status, c, cyc, Ucur, wcur, preC, Unext, wnext);
-      prefetch_here(2);
-      run_stage<false, false>(P, P.st[1], 1, p, c.x, c.y, c.th, false, 0.0, gslot, bs, status, f, cyc2, Ucur, wcur, preF, Unext, wnext);
+      run_stage<false, false>(P, P.st[0], 0, p, x, y, th, sample, u, gslot, bs, status, c, cyc, Ucur, wcur, 0u);
+      run_stage<false, false>(P, P.st[1], 1, p, c.x, c.y, c.th, false, 0.0, gslot, bs, status, f, cyc2, Ucur, wcur, uEmpty);
     }
-    prefetch_here(4);
-    status = csync_or(status);
+    status = block_or(status, bs);
     if (threadIdx.x == 0) {
       P.outPose[3 * p] = f.x; P.outPose[3 * p + 1] = f.y; P.outPose[3 * p + 2] = f.th;
       P.outConf[p] = c.conf;
       int* o = P.outIdx + 6 * p;
       o[0] = c.it; o[1] = c.ia; o[2] = c.ib; o[3] = f.it; o[4] = f.ia; o[5] = f.ib;
-      P.status[p] = status;
+      P.status[p] |= status;     // OR: bits raised earlier in the step (slam_propose_poses) survive
     }
   }
 }
@@ -1185,12 +1251,22 @@ __global__ void priors_kernel(int N, int nHalf, double coef, const double* phi, 
 // ------------------------------------------------------------------------------------------------ host
 using namespace slam;
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
 struct slam_matcher {
   MatchParams P;
   std::vector<void*> owned;
   size_t smemBytes;
   int numCtas;
   size_t workspaceBytes;
+  int device = -1;           // device the handle was created on (tables live there)
+  bool attrSet = false;      // dynamic shared-memory opt-in done for this handle's device
+  EncodeTiledFn encode = nullptr;
+  alignas(64) CUtensorMap tmap;
+  const void* tmapGrid = nullptr;
+  int tmapN = 0;
 };
 
 static void leaves_rec(int off, int n, std::vector<int2>& leaves, std::vector<short>& prog) {
@@ -1367,7 +1443,27 @@ extern "C" int slam_matcher_create(const slam_geometry* g, const slam_matcher_de
     sms = 148;
     cudaGetLastError();
   }
-  const size_t budget = (size_t)smemMax - 1024;   // static shared + reserve
+  // union window geometry first: the TMA ring needs RING_STAGES stages of >= 1 window row next to the stage buffers
+  const double coarseReach = d->coarse.nHalf * d->coarse.unitLength;
+  P.RU = d->windowRadius + coarseReach + 2.0 * g->unit;
+  P.UWcells = (((int)(2.0 * P.RU / g->unit) + 8) + 63) / 64 * 64;     // multiple of 64 cells (2 bitmap words)
+  P.UW = 2 * (P.UWcells / 64);
+  P.URows = std::min((int)(2.0 * P.RU / g->unit) + 8, g->G);
+  {
+    const int m64 = P.UWcells / 64;
+    int dsel = 1;
+    for (int dd = 1; dd <= 4; ++dd)
+      if (m64 % dd == 0) dsel = dd;
+    P.boxCells = 64 * dsel;                                          // TMA box: <= 256 elements per dimension
+    P.nBoxes = m64 / dsel;
+  }
+  const size_t rowBytes = (size_t)P.UWcells * 8;
+  const size_t staticReserve = 4096;                                // static shared memory + driver reserve
+  if ((size_t)smemMax < staticReserve + RING_STAGES * rowBytes + 128 + 16384) {
+    slam_matcher_destroy(m);
+    return fail(SLAM_E_UNSUPPORTED, "union window row too large for the shared-memory TMA ring");
+  }
+  const size_t budget = (size_t)smemMax - staticReserve - RING_STAGES * rowBytes - 128;
   size_t smemNeed = 0, slot = 0;
   bool fast = true;
   for (int attempt = 0; attempt < 2; ++attempt) {
@@ -1382,22 +1478,21 @@ extern "C" int slam_matcher_create(const slam_geometry* g, const slam_matcher_de
     return rc;
   }
   P.fast = fast ? 1 : 0;
-  // background stream: union window geometry, 2-stage ring after everything else, two union bitmaps in the slot
+  // TMA ring after the stage buffers: as many window rows per stage as fit (<= 4), two union bitmaps in the slot
   {
-    const double coarseReach = d->coarse.nHalf * d->coarse.unitLength;
-    P.RU = d->windowRadius + coarseReach + 2.0 * g->unit;
-    P.UWcells = (((int)(2.0 * P.RU / g->unit) + 8) + 63) / 64 * 64;     // multiple of 64 cells (2 bitmap words)
-    P.UWcells = std::min(P.UWcells, (g->pitch / 2) * 2);
-    P.UW = 2 * ((P.UWcells + 63) / 64);
-    P.URows = std::min((int)(2.0 * P.RU / g->unit) + 8, g->G);
-    P.ringRows = 0;
-    P.oRing = 0;
+    const size_t avail = (size_t)smemMax - staticReserve - smemNeed - 128;
+    int by = (int)(avail / (RING_STAGES * rowBytes));
+    by = std::max(1, std::min(by, 4));
+    P.ringRows = by;
+    P.oRing = (int)align_up(smemNeed, 128);
+    smemNeed = (size_t)P.oRing + 128 + (size_t)RING_STAGES * by * rowBytes;
     P.gU = align_up(slot, 256);
     slot = P.gU + 2 * (size_t)P.URows * P.UW * 4;     // double buffered: next particle's bitmap is built early
   }
   m->smemBytes = smemNeed;
   P.slotBytes = align_up(slot, 256);
   m->numCtas = sms;
+  m->device = dev;
   m->workspaceBytes = P.slotBytes * (size_t)m->numCtas + 256;
   *out = m;
   return 0;
@@ -1446,19 +1541,41 @@ extern "C" int slam_match_scan(slam_matcher* m, const float* d_grid, int32_t N, 
     P.dbgVol[s] = debug ? debug->d_vol[s] : nullptr;
     if (P.dbgProb[s] && !P.dbgDims[s]) return fail(SLAM_E_BADARG, "d_prob needs d_probDims");
   }
-  static bool attrSet = false;
-  if (!attrSet) {
-    int dev = 0, optin = 0;
-    SLAM_CUDA(cudaGetDevice(&dev));
+  int dev = 0;
+  SLAM_CUDA(cudaGetDevice(&dev));
+  if (dev != m->device) return fail(SLAM_E_BADARG, "slam_match_scan: the current device is not the one the matcher was created on");
+  if (!m->attrSet) {
+    int optin = 0;
     SLAM_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     cudaFuncAttributes fa;
     SLAM_CUDA(cudaFuncGetAttributes(&fa, match_kernel));
+    if (m->smemBytes + fa.sharedSizeBytes > (size_t)optin) return fail(SLAM_E_UNSUPPORTED, "slam_match_scan: shared-memory plan exceeds the device limit");
     SLAM_CUDA(cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    optin - (int)fa.sharedSizeBytes));
-    attrSet = true;
+    m->attrSet = true;
+  }
+  // TMA descriptor of the lattice batch: [N][G][pitch] cells of 8 bytes, box = boxCells x ringRows x 1
+  if (m->tmapGrid != (const void*)d_grid || m->tmapN != N) {
+    if (!m->encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      SLAM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      if (!fn || qres != cudaDriverEntryPointSuccess) return fail(SLAM_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available in this driver");
+      m->encode = (EncodeTiledFn)fn;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)P.pitch, (cuuint64_t)P.G, (cuuint64_t)N};
+    const cuuint64_t strides[2] = {(cuuint64_t)P.pitch * 8, (cuuint64_t)P.pitch * 8 * (cuuint64_t)P.G};
+    const cuuint32_t box[3] = {(cuuint32_t)P.boxCells, (cuuint32_t)P.ringRows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult rc = m->encode(&m->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void*)d_grid, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail(SLAM_E_UNSUPPORTED, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)rc) + ")");
+    m->tmapGrid = d_grid;
+    m->tmapN = N;
   }
   const int grid = std::min(N, m->numCtas);
-  match_kernel<<<grid, NT, m->smemBytes, (cudaStream_t)stream>>>(P);
+  match_kernel<<<grid, NT_ALL, m->smemBytes, (cudaStream_t)stream>>>(P, m->tmap);
   SLAM_CUDA(cudaGetLastError());
   return 0;
 }

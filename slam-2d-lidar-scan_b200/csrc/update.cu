@@ -221,24 +221,19 @@ extern "C" int slam_grid_init(const slam_geometry* g, float* d_grid, int32_t N, 
   return 0;
 }
 
-static int4* g_prep = nullptr;   // per-process scratch for the preparation pass (grown on demand)
-static int* g_slow = nullptr;
-static int g_prepCap = 0;
-
 extern "C" int slam_update_grid(const slam_geometry* g, float* d_grid, int32_t N, const double* d_ranges,
                                 const double* d_pose, int32_t* d_status, void* stream) {
   if (!g || !d_grid || !d_ranges || !d_pose || !d_status) return fail(SLAM_E_BADARG, "slam_update_grid: null argument");
   if (N <= 0) return 0;
   if (g->K > SLAM_MAX_BEAMS) return fail(SLAM_E_UNSUPPORTED, "too many beams");
   cudaStream_t st = (cudaStream_t)stream;
-  if (N > g_prepCap) {
-    if (g_prep) cudaFree(g_prep);
-    if (g_slow) cudaFree(g_slow);
-    g_prep = nullptr; g_slow = nullptr; g_prepCap = 0;
-    SLAM_CUDA(cudaMalloc(&g_prep, (size_t)N * sizeof(int4)));
-    SLAM_CUDA(cudaMalloc(&g_slow, ((size_t)N + 1) * sizeof(int)));
-    g_prepCap = N;
-  }
+  // per-call, stream-ordered scratch on the current device (no process-global state: several grids / streams /
+  // devices may call concurrently): [N] int4 preparation records + 1 + N ints of slow-path work list
+  const size_t prepBytes = ((size_t)N * sizeof(int4) + 255) / 256 * 256;
+  unsigned char* scratch = nullptr;
+  SLAM_CUDA(cudaMallocAsync((void**)&scratch, prepBytes + ((size_t)N + 1) * sizeof(int), st));
+  int4* g_prep = reinterpret_cast<int4*>(scratch);
+  int* g_slow = reinterpret_cast<int*>(scratch + prepBytes);
   SLAM_CUDA(cudaMemsetAsync(g_slow, 0, sizeof(int), st));
   UpdParams P;
   P.G = g->G; P.pitch = g->pitch; P.K = g->K; P.L = g->L; P.numSpokes = g->numSpokes; P.start = g->spokesStartIdx; P.N = N;
@@ -258,5 +253,6 @@ extern "C" int slam_update_grid(const slam_geometry* g, float* d_grid, int32_t N
     update_general_kernel<<<grid, 256, 2 * g->L * sizeof(int), st>>>(P);
     SLAM_CUDA(cudaGetLastError());
   }
+  SLAM_CUDA(cudaFreeAsync(scratch, st));
   return 0;
 }

@@ -14,7 +14,7 @@ import torch
 import torch.distributed as dist
 
 from . import _native as nat
-from .engine import raise_for_status, _stream
+from .engine import StepResult, raise_for_status, _stream
 from .fastslam import ParticleFilter
 
 
@@ -51,10 +51,15 @@ class ShardedParticleFilter:
         self.lo, self.hi = shard_bounds(numParticles, self.world)[self.rank]
         self.local = ParticleFilter(self.hi - self.lo, ogParameters, smParameters, device=device)
         dev = self.local.geom.device
-        self._mine = torch.zeros((self.hi - self.lo, 4), dtype=torch.float64, device=dev)
-        self._all = torch.zeros((numParticles, 4), dtype=torch.float64, device=dev)
+        nL = self.hi - self.lo
+        # all-gather payload per rank: nL rows (unnormalised weight, x, y, theta) + one row carrying the OR of the
+        # rank's status words, so that every rank raises the same exception in the same step (no hung collectives)
+        self._mine = torch.zeros((nL + 1, 4), dtype=torch.float64, device=dev)
+        self._all = torch.zeros((self.world, nL + 1, 4), dtype=torch.float64, device=dev)
+        self._stRanks = torch.zeros(self.world, dtype=torch.int32, device=dev)
         self._w = torch.zeros(numParticles, dtype=torch.float64, device=dev)
-        self._out = torch.zeros(4, dtype=torch.float64, device=dev)
+        self._res = StepResult(dev)
+        self._out = self._res.out
         self._cdf = torch.zeros(numParticles, dtype=torch.float64, device=dev)
         self._ridx = torch.zeros(numParticles, dtype=torch.int32, device=dev)
         self.lastVariance = None
@@ -67,29 +72,35 @@ class ShardedParticleFilter:
     def gather_and_normalize(self):
         """The step's single collective + the replicated sequential normalisation.  No host synchronisation."""
         pf = self.local
-        self._mine[:, 0] = pf.weights
-        self._mine[:, 1:] = pf.prevMatched
+        nL, dev = self.hi - self.lo, pf.geom.device
+        pf._res.reduce_status(pf.status, dev)
+        self._mine[:nL, 0] = pf.weights
+        self._mine[:nL, 1:] = pf.prevMatched
+        self._mine[nL, 0:1] = pf._res.bits.to(torch.float64)
         if self.world > 1:
-            dist.all_gather_into_tensor(self._all, self._mine, group=self.group)
+            dist.all_gather_into_tensor(self._all.view(-1, 4), self._mine, group=self.group)
         else:
-            self._all.copy_(self._mine)
-        self._w.copy_(self._all[:, 0])
-        nat.check(nat.lib.slam_normalize_weights(self.numParticles, self._w.data_ptr(), self._out.data_ptr(),
-                                                 _stream(pf.geom.device)))
-        pf.kernelLaunches += 1
+            self._all[0].copy_(self._mine)
+        self._w.copy_(self._all[:, :nL, 0].reshape(-1))
+        self._stRanks.copy_(self._all[:, nL, 0])
+        with torch.cuda.device(dev):
+            nat.check(nat.lib.slam_normalize_weights(self.numParticles, self._w.data_ptr(), self._out.data_ptr(),
+                                                     _stream(dev)))
+        self._res.reduce_status(self._stRanks, dev)
+        pf.kernelLaunches += 3
         pf.weights.copy_(self._w[self.lo:self.hi])
 
     def weightUnbalanced(self):
         self.gather_and_normalize()
-        out = torch.cat([self._out[:2], self.local.status.max().to(torch.float64).view(1)]).cpu()
+        var, fired, bits = self._res.fetch()
         self.local.d2hBytes += 24
-        raise_for_status(int(out[2].item()))
-        self.lastVariance = float(out[0].item())
-        return bool(out[1].item() != 0.0)
+        raise_for_status(bits)
+        self.lastVariance = var
+        return fired
 
     def poses(self):
         """[N][3] poses of all particles as of the last gather (host numpy)."""
-        return self._all[:, 1:].cpu().numpy()
+        return self._all[:, :self.hi - self.lo, 1:].reshape(-1, 3).cpu().numpy()
 
     def resample(self):
         """Global multinomial resample (FastSlam.py:50-62); lattices whose source lives on another rank move P2P."""

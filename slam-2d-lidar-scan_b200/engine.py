@@ -150,13 +150,15 @@ class MatcherEngine:
 
     def match(self, grids, n, d_ranges, d_estPose, d_rv, d_tw, d_uniforms, d_outPose, d_outConf, d_outIdx, d_status,
               debug=None):
-        """slam_match_scan on the current stream.  All arguments are device tensors (or None)."""
+        """slam_match_scan on the geometry's device, current stream.  All arguments are device tensors (or None).
+        Status bits are OR-ed into d_status (sticky)."""
         dev = self.geom.device
-        nat.check(nat.lib.slam_match_scan(
-            self.handle, grids.data_ptr(), n, d_ranges.data_ptr(), d_estPose.data_ptr(), d_rv.data_ptr(), _ptr(d_tw),
-            _ptr(d_uniforms), d_outPose.data_ptr(), d_outConf.data_ptr(), d_outIdx.data_ptr(), d_status.data_ptr(),
-            self.workspace.data_ptr(), self.workspace.numel(), C.byref(debug) if debug is not None else None,
-            _stream(dev)))
+        with torch.cuda.device(dev):
+            nat.check(nat.lib.slam_match_scan(
+                self.handle, grids.data_ptr(), n, d_ranges.data_ptr(), d_estPose.data_ptr(), d_rv.data_ptr(), _ptr(d_tw),
+                _ptr(d_uniforms), d_outPose.data_ptr(), d_outConf.data_ptr(), d_outIdx.data_ptr(), d_status.data_ptr(),
+                self.workspace.data_ptr(), self.workspace.numel(), C.byref(debug) if debug is not None else None,
+                _stream(dev)))
 
     def volume_shape(self, stage):
         n = 2 * self.stageInfo[stage]["nHalf"] + 1
@@ -164,5 +166,26 @@ class MatcherEngine:
 
 
 def update_grids(geom, grids, n, d_ranges, d_pose, d_status):
-    nat.check(nat.lib.slam_update_grid(geom.c, grids.data_ptr(), n, d_ranges.data_ptr(), d_pose.data_ptr(),
-                                       d_status.data_ptr(), _stream(geom.device)))
+    with torch.cuda.device(geom.device):
+        nat.check(nat.lib.slam_update_grid(geom.c, grids.data_ptr(), n, d_ranges.data_ptr(), d_pose.data_ptr(),
+                                           d_status.data_ptr(), _stream(geom.device)))
+
+
+class StepResult:
+    """[variance, trigger] (float64) + OR of the status words (int32) in ONE 24-byte device buffer, so that
+    weightUnbalanced needs a single device-to-host copy."""
+
+    def __init__(self, dev):
+        self.raw = torch.zeros(32, dtype=torch.uint8, device=dev)
+        self.out = self.raw.view(torch.float64)          # [4]: variance, trigger, (status bits), -
+        self.bits = self.raw.view(torch.int32)[4:5]      # low word of out[2]
+
+    def reduce_status(self, status, dev):
+        with torch.cuda.device(dev):
+            nat.check(nat.lib.slam_status_reduce(status.numel(), status.data_ptr(), self.bits.data_ptr(), _stream(dev)))
+
+    def fetch(self):
+        """-> (variance, fired, statusBits); synchronises."""
+        h = self.raw[:24].cpu()
+        v = h[:16].view(torch.float64)
+        return float(v[0].item()), bool(v[1].item() != 0.0), int(h[16:20].view(torch.int32).item())

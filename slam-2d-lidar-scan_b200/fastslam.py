@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _native as nat
-from .engine import MatcherEngine, raise_for_status, update_grids, _stream
+from .engine import MatcherEngine, StepResult, raise_for_status, update_grids, _stream
 from .geometry import LidarGeometry
 from .grid import OccupancyGrid
 from .matcher import ScanMatcher
@@ -105,7 +105,8 @@ class ParticleFilter:
         self._stage_d = torch.zeros(K + n + n2, **f64)
         self._stage_ev = torch.cuda.Event()
         self._stage_busy = False
-        self._out = torch.zeros(4, **f64)
+        self._res = StepResult(dev)
+        self._out = self._res.out
         self._cdf = torch.zeros(n, **f64)
         self._ridx = torch.zeros(n, **i32)
         self._traj = []
@@ -142,11 +143,13 @@ class ParticleFilter:
     def weightUnbalanced(self):
         """Normalise, then the reference's variance trigger (FastSlam.py:30-41).  Synchronises (returns a bool)."""
         self._normalize()
-        out = torch.cat([self._out[:2], self.status.max().to(torch.float64).view(1)]).cpu()
+        self._res.reduce_status(self.status, self.geom.device)
+        self.kernelLaunches += 1
+        var, fired, bits = self._res.fetch()
         self.d2hBytes += 24
-        raise_for_status(int(out[2].item()))
-        self.lastVariance = float(out[0].item())
-        return bool(out[1].item() != 0.0)
+        raise_for_status(bits)
+        self.lastVariance = var
+        return fired
 
     def resample(self):
         """np.random.choice(arange(N), N, p=weights) + deep copy of the chosen particles (FastSlam.py:50-62)."""
@@ -174,8 +177,9 @@ class ParticleFilter:
 
     # ---- device step
     def _normalize(self):
-        nat.check(nat.lib.slam_normalize_weights(self.numParticles, self.weights.data_ptr(), self._out.data_ptr(),
-                                                 _stream(self.geom.device)))
+        with torch.cuda.device(self.geom.device):
+            nat.check(nat.lib.slam_normalize_weights(self.numParticles, self.weights.data_ptr(), self._out.data_ptr(),
+                                                     _stream(self.geom.device)))
         self.kernelLaunches += 1
 
     def _prepare(self, reading, count, n, prevRaw, prevRawHeading, out=None, uniforms=None):
@@ -204,6 +208,10 @@ class ParticleFilter:
 
     def _launch(self, lo, hi, rec, d_stage):
         """Device part of Particle.update for particles [lo, hi): kernel launches only, no host synchronisation."""
+        with torch.cuda.device(self.geom.device):
+            self._launch_on_device(lo, hi, rec, d_stage)
+
+    def _launch_on_device(self, lo, hi, rec, d_stage):
         n, dev, K, N = hi - lo, self.geom.device, self.geom.numSamplesPerRev, self.numParticles
         st = _stream(dev)
         eng = self.engine

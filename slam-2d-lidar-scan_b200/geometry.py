@@ -91,5 +91,6 @@ class LidarGeometry:
     def new_grids(self, n):
         """[n][G][pitch][2] float32 lattices initialised to (visited, total) = (1, 2) (:13-14)."""
         g = torch.empty((n, self.G, self.pitch, 2), dtype=torch.float32, device=self.device)
-        nat.check(nat.lib.slam_grid_init(self.c, g.data_ptr(), n, torch.cuda.current_stream(self.device).cuda_stream))
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib.slam_grid_init(self.c, g.data_ptr(), n, torch.cuda.current_stream(self.device).cuda_stream))
         return g

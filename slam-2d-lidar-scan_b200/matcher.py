@@ -57,6 +57,7 @@ class ScanMatcher:
             # np.random.choice(arange(n), 1, p=...) draws exactly one double from the legacy global RandomState
             self._u.copy_(torch.from_numpy(np.random.random_sample(1)))
             u = self._u
+        self._status.zero_()        # the kernels OR their bits in; this standalone matcher reports per call
         dbg = bufs = None
         if self.debug:
             dbg, bufs = eng.debug_buffers(1)

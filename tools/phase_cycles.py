@@ -44,12 +44,12 @@ for count, fr in enumerate(scene["frames"][:6], start=1):
 torch.cuda.synchronize()
 ms = [a.elapsed_time(b) for a, b in pf.matchEvents]
 c = cyc.cpu().numpy().astype(np.float64)
-names = ["window", "blur+clamp", "points", "lists(sort)", "correlate", "select", "-", "-"]
+names = ["window", "blur+clamp", "points", "lists(sort)", "correlate", "select", "wait-union", "-"]
 per = c.sum(0) / (2 * n)           # two timed launches
 tot = per.sum()
 print("match kernel ms per launch:", ms)
 for st in range(2):
-    for k in range(6):
+    for k in range(7 if st == 0 else 6):
         v = per[8 * st + k]
         print("%-7s %-12s %10.0f cycles/particle  %5.1f %%" % ("coarse" if st == 0 else "fine", names[k], v, 100 * v / tot))
 print("total %.0f cycles/particle; status max %d" % (tot, int(pf.status.max().item())))
