@@ -149,7 +149,9 @@ int slam_grid_init(const slam_geometry* geom, float* d_grid, int32_t N, void* st
  * cell is written by exactly one thread, reproducing numpy's once-per-statement fancy `+=` even when two
  * lidar-local cells round to the same map cell.  d_pose [N][3]; d_status |= SLAM_ST_SCAN_OUTSIDE_MAP. */
 int slam_update_grid(const slam_geometry* geom, float* d_grid, int32_t N, const double* d_ranges,
-                     const double* d_pose, int32_t* d_status, void* stream);
+                     const double* d_pose, int32_t* d_status, void* d_workspace, size_t workspaceBytes, void* stream);
+/* Device scratch slam_update_grid needs for N particles (per call; may be shared by calls on one stream). */
+size_t slam_update_workspace_bytes(int32_t N);
 
 /* Per-particle odometry proposal (FastSlam.py:77-106).  The raw-odometry part is identical for every
  * particle and is computed by the host: estTheta = (prevMatched.theta + rawTheta) - prevRawTheta (left to

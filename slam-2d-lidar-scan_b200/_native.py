@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libslam2d_b200.so")
+LIB_PATH = os.environ.get("SLAM2D_B200_LIB") or os.path.join(_HERE, "libslam2d_b200.so")   # env: A/B builds of the kernels
 
 MAX_BLUR_RADIUS = 8
 MAX_BEAMS = 512
@@ -57,7 +57,8 @@ SYMBOLS = {
     "slam_match_scan": (C.c_int, [_V, _V, _I, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _Z, C.POINTER(MatchDebug), _V]),
     "slam_motion_priors": (C.c_int, [_I, _I, _D, _V, _V, _V, _V]),
     "slam_grid_init": (C.c_int, [C.POINTER(Geometry), _V, _I, _V]),
-    "slam_update_grid": (C.c_int, [C.POINTER(Geometry), _V, _I, _V, _V, _V, _V]),
+    "slam_update_grid": (C.c_int, [C.POINTER(Geometry), _V, _I, _V, _V, _V, _V, _Z, _V]),
+    "slam_update_workspace_bytes": (_Z, [_I]),
     "slam_propose_poses": (C.c_int, [_I, _V, _D, _D, _I, _D, _V, _V, _V, _V, _V, _V, _V]),
     "slam_finish_step": (C.c_int, [_I, _V, _V, _V, _V, _V, _V, _V]),
     "slam_normalize_weights": (C.c_int, [_I, _V, _V, _V]),

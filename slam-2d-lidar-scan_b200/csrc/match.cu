@@ -27,13 +27,25 @@
 
 namespace slam {
 
-constexpr int NT = 480;          // compute threads per CTA: 15 warps + the stream warp = 16 warps x 128 registers (4 per scheduler)
+#ifndef SLAM_STREAM_WARPS
+#define SLAM_STREAM_WARPS 2
+#endif
+constexpr int NSW = SLAM_STREAM_WARPS;   // stream warps: TMA producers / occupancy-bit packers of the union window.  The
+                                 // shared-memory pipe serves warps round-robin, so a stream warp reads its ring at 1/16
+                                 // of the pipe (measured): NSW sets the stream rate (2.5 MB per particle at c3)
+constexpr int NT = 512 - 32 * NSW;   // compute threads per CTA: 16 warps x 128 registers in all (4 per scheduler)
 constexpr int NW = NT / 32;      // compute warps per CTA
 constexpr int NWC = NW;          // compute warps
 constexpr int NTC = NWC * 32;    // compute threads
-constexpr int NT_ALL = NTC + 32; // + one stream warp: TMA producer / occupancy-bit packer of the union window
+constexpr int NT_ALL = 512;
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int RING_STAGES = 4;   // TMA ring depth (stages of ringRows window rows each)
+constexpr int RING_STAGES = 4;   // TMA ring depth over all stream warps (stages of ringRows window rows each)
+constexpr int RING_PER_WARP = RING_STAGES / NSW;
+static_assert(RING_STAGES % NSW == 0 && RING_PER_WARP >= 1, "ring stages must split evenly over the stream warps");
+
+// Warp 0 is the stream warp (lowest warp id: the schedulers favour older warps, and the stream must never starve);
+// compute threads are numbered from 0 by ctid().
+__device__ __forceinline__ int ctid() { return (int)threadIdx.x - 32 * NSW; }
 
 // barrier over the compute warps (named barrier 1)
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory"); }
@@ -65,6 +77,8 @@ struct StageDev {
   int Wmax, Wmap, words, WT, Ppitch, TB, Kpad, E;   // words includes >= 1 always-zero spare word per row
   int bitsInSmem, PInSmem, scoresInSmem, needScores;
   int oBits, oBitsT, oDil, oVw, oRow, oCol, oTiles, oP, oLists, oCnt, oScores, oDx, oDy, oLeaf;
+  int tileCap;                 // capacity of one warp's private segment of the active-tile list
+  int oAux, auxPitch, auxOK;   // range-path tables (4 x auxPitch shorts) + row buffer [Wmax][UW] words, if they fit
   size_t gBits, gBitsT, gDil, gTiles, gP, gScores;  // byte offsets inside a CTA's global scratch slot
 };
 
@@ -82,8 +96,10 @@ struct MatchParams {
   double* dbgProb[2];
   int* dbgDims[2];
   double* dbgVol[2];
-  long long* dbgCycles;  // [gridDim][16] or null
+  long long* dbgCycles;  // [gridDim][48] or null
   int forceExactCdf;
+  int forceGenericScatter;   // test hook: always take the atomicOr scatter path
+  int noPrune;               // test hook: evaluate every fine hypothesis completely (no branch-and-bound)
   int fast;              // plan: 1 = shared-memory plan for both stages, 0 = global-slot plan
   // background window stream (union of the coarse and every possible fine window, read once)
   double RU;             // union half size = R + coarse search radius + margin
@@ -211,10 +227,21 @@ struct FetchGated {
   }
 };
 
+// Exact branch-and-bound for the argmax-only (fine) stage.  Field values are <= 0 and IEEE addition is monotone, so
+// the pairwise tree over the CURRENT lane sums (plus the finished first half, if any) is an upper bound of the
+// hypothesis' final score; once it is strictly below the best finished score of the block (the incumbent, shared
+// memory), the hypothesis can neither win nor tie the first-maximum rule and its remaining gathers are skipped.
+struct PruneCtx {
+  unsigned bestS;      // shared address of the incumbent score (double, <= 0)
+  double a1[GRP];      // finished first half of the top-level split
+  int h1;              // a1 is valid
+  int validMask;       // which of the GRP sums are real hypotheses
+};
+
 // numpy pairwise_sum for GRP independent sums sharing the index stream: n <= 128 branch inline, recursion
 // (split at n/2 rounded down to a multiple of 8, depth <= 3 for n <= 512) as nested loops around ONE leaf body.
-template <class F>
-__device__ __forceinline__ void leaf_sum_g(const F& f, int off, int n, double (&out)[GRP]) {
+template <bool PRUNE, class F>
+__device__ __forceinline__ bool leaf_sum_g(const F& f, int off, int n, double (&out)[GRP], const PruneCtx& pc) {
   if (n < 8) {
 #pragma unroll
     for (int g = 0; g < GRP; ++g) out[g] = 0.0;
@@ -224,7 +251,7 @@ __device__ __forceinline__ void leaf_sum_g(const F& f, int off, int n, double (&
 #pragma unroll
       for (int g = 0; g < GRP; ++g) out[g] = dadd(out[g], v[g]);
     }
-    return;
+    return false;
   }
   double r[8][GRP];
 #pragma unroll
@@ -239,6 +266,17 @@ __device__ __forceinline__ void leaf_sum_g(const F& f, int off, int n, double (&
 #pragma unroll
       for (int g = 0; g < GRP; ++g) r[l][g] = dadd(r[l][g], v[l][g]);
     }
+    if (PRUNE && (i & 8)) {                                       // every 16 points
+      const double inc = lds_f64(pc.bestS);
+      bool all = true;
+#pragma unroll
+      for (int g = 0; g < GRP; ++g) {
+        double x = dadd(dadd(dadd(r[0][g], r[1][g]), dadd(r[2][g], r[3][g])), dadd(dadd(r[4][g], r[5][g]), dadd(r[6][g], r[7][g])));
+        if (pc.h1) x = dadd(pc.a1[g], x);
+        if (((pc.validMask >> g) & 1) && !(x < inc)) all = false;
+      }
+      if (all) return true;
+    }
   }
 #pragma unroll
   for (int g = 0; g < GRP; ++g)
@@ -249,6 +287,7 @@ __device__ __forceinline__ void leaf_sum_g(const F& f, int off, int n, double (&
 #pragma unroll
     for (int g = 0; g < GRP; ++g) out[g] = dadd(out[g], v[g]);
   }
+  return false;
 }
 
 __device__ __forceinline__ int pw_split(int n) {   // numpy: n2 = n / 2; n2 -= n2 % 8
@@ -256,14 +295,21 @@ __device__ __forceinline__ int pw_split(int n) {   // numpy: n2 = n / 2; n2 -= n
   return n2 - (n2 % 8);
 }
 
-template <class F>
-__device__ __forceinline__ void pairwise_g(const F& f, int n, double (&out)[GRP]) {
+// returns true if the hypothesis group was pruned (out is then undefined)
+template <bool PRUNE, class F>
+__device__ __forceinline__ bool pairwise_g(const F& f, int n, double (&out)[GRP], PruneCtx& pc) {
   const int c1 = n > 128 ? 2 : 1;
+  pc.h1 = 0;
   for (int i1 = 0; i1 < c1; ++i1) {
     const int s1 = c1 == 2 ? pw_split(n) : n;
     const int o1 = i1 ? s1 : 0, n1 = c1 == 2 ? (i1 ? n - s1 : s1) : n;
     const int c2 = n1 > 128 ? 2 : 1;
     double acc2[GRP];
+    if (PRUNE && i1) {
+#pragma unroll
+      for (int g = 0; g < GRP; ++g) pc.a1[g] = out[g];
+      pc.h1 = 1;
+    }
     for (int i2 = 0; i2 < c2; ++i2) {
       const int s2 = c2 == 2 ? pw_split(n1) : n1;
       const int o2 = o1 + (i2 ? s2 : 0), n2 = c2 == 2 ? (i2 ? n1 - s2 : s2) : n1;
@@ -273,7 +319,7 @@ __device__ __forceinline__ void pairwise_g(const F& f, int n, double (&out)[GRP]
         const int s3 = c3 == 2 ? pw_split(n2) : n2;
         const int o3 = o2 + (i3 ? s3 : 0), n3 = c3 == 2 ? (i3 ? n2 - s3 : s3) : n2;
         double leaf[GRP];
-        leaf_sum_g(f, o3, n3, leaf);          // n3 <= 128 for n <= 512
+        if (leaf_sum_g<PRUNE>(f, o3, n3, leaf, pc)) return true;          // n3 <= 128 for n <= 512
 #pragma unroll
         for (int g = 0; g < GRP; ++g) acc3[g] = i3 ? dadd(acc3[g], leaf[g]) : leaf[g];
       }
@@ -283,6 +329,7 @@ __device__ __forceinline__ void pairwise_g(const F& f, int n, double (&out)[GRP]
 #pragma unroll
     for (int g = 0; g < GRP; ++g) out[g] = i1 ? dadd(out[g], acc2[g]) : acc2[g];
   }
+  return false;
 }
 
 // numpy pairwise_sum, n <= 128 branch (8 running lanes, fixed tree, sequential tail)
@@ -418,11 +465,13 @@ struct BlockScratch {
   double dval[NWC];
   int ival[NWC];
   double bcast[4];
+  double incumbent;                // branch-and-bound: best finished score of the fine stage so far
   int ibcast[8];
+  unsigned maskA[64], maskB[64];   // per union-bitmap word: window columns whose index-map offset is D / D-1
 };
 
 __device__ __forceinline__ double block_min(double v, BlockScratch& bs) {
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int lane = ctid() & 31, warp = ctid() >> 5;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, d));
   csync();
@@ -438,20 +487,34 @@ __device__ __forceinline__ double block_min(double v, BlockScratch& bs) {
 __device__ __forceinline__ int block_or(int v, BlockScratch& bs) {
   v = __reduce_or_sync(FULL, v);
   csync();
-  if ((threadIdx.x & 31) == 0) bs.ival[threadIdx.x >> 5] = v;
+  if ((ctid() & 31) == 0) bs.ival[ctid() >> 5] = v;
   csync();
   int r = 0;
   for (int i = 0; i < NWC; ++i) r |= bs.ival[i];
   return r;
 }
 
-constexpr int TPI = 2;   // active tiles a warp blurs at a time (independent dependency chains interleave)
+// sub-phase cycle accounting (profiling hook): thread 0 of the compute warps accumulates the time since the last mark
+struct SubCyc {
+  long long* slot;
+  long long last;
+  __device__ __forceinline__ void start(long long* s) { slot = s; if (slot && ctid() == 0) last = clock64(); }
+  __device__ __forceinline__ void mark(int i) {
+    if (slot && ctid() == 0) { const long long t = clock64(); slot[i] += t - last; last = t; }
+  }
+};
+
+constexpr int TPI = 2;   // generic-radius path: active tiles a warp blurs at a time
+constexpr int TG = 4;    // templated-radius path: tiles per warp iteration (8 lanes x 4 cells each in the second pass)
+constexpr int VW_PER_WARP = 192;   // doubles of first-pass values per warp: max(TG * (32 + 2*8), TPI * 64)
 
 // ---- separable blur (phase D) templated on the radius so every tap loop unrolls and its loads pipeline.
 // RT == 0: generic run-time radius.  Returns (through refs) the running minimum and the number of active cells.
 template <int RT, bool FAST, bool DENSE>
 __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot, int Pp, int Wx, int Wy, int* counter,
-                                        double& mnOut, int& activeOut, double& thrOut) {
+                                        double& mnOut, int& activeOut, double& thrOut, long long* subSlots) {
+  SubCyc sc;
+  sc.start(subSlots);
   __shared__ double s_w[2 * SLAM_MAX_BLUR_RADIUS + 1];
   __shared__ int s_active[NWC];
   const unsigned* bits = buf<FAST, unsigned>(S.oBits, gslot, S.gBits);
@@ -459,14 +522,19 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
   unsigned* dil = buf<FAST, unsigned>(S.oDil, gslot, S.gDil);
   double* Pf = DENSE ? sbuf<double>(S.oP) : reinterpret_cast<double*>(gslot + S.gP);
   double* VwAll = sbuf<double>(S.oVw);
-  unsigned* tiles = buf<FAST, unsigned>(S.oTiles, gslot, S.gTiles);   // ids of the active tiles (order irrelevant)
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned short* tiles = buf<FAST, unsigned short>(S.oTiles, gslot, S.gTiles);   // ids of the active tiles (order irrelevant)
+  const int tid = ctid(), lane = tid & 31, warp = tid >> 5;
   const int r = RT ? RT : S.r;
   const int words = S.words, WT = S.WT;
   if (tid <= 2 * r) s_w[tid] = S.w[tid];
-  if (tid == 0) { counter[0] = 0; counter[1] = 0; }
+  (void)counter;
   csync();
   int myActive = 0;
+  // Every warp appends the active tiles of its rows to a private segment of the list and blurs them itself
+  // (rows are dealt out round-robin, so the segments balance): no shared-memory atomics -- contended
+  // same-address atomics cost ~64 cycles each and used to dominate this phase.
+  unsigned short* myTiles = tiles + (size_t)warp * S.tileCap;
+  int myCount = 0;
   // D1. activity bitmap: cell (i, j) is active iff an occupied cell lies within +-r rows and +-r columns
   //     (reflected taps always fall inside that span, so plain dilation is exact).
   if (words <= 32) {
@@ -479,8 +547,15 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
       if (i < Wy && w < words) {
         if (i - r >= 0 && i + r < Wy) {                  // interior: no reflection, unit-stride rows
           const unsigned* q = bits + (i - r) * words + w;
+          unsigned va = 0u, vb = 0u, vc = 0u, vd = 0u;     // four OR chains instead of one
 #pragma unroll
-          for (int d = 0; d <= 2 * r; ++d) v |= q[d * words];
+          for (int d = 0; d <= 2 * r; d += 4) {
+            va |= q[d * words];
+            if (d + 1 <= 2 * r) vb |= q[(d + 1) * words];
+            if (d + 2 <= 2 * r) vc |= q[(d + 2) * words];
+            if (d + 3 <= 2 * r) vd |= q[(d + 3) * words];
+          }
+          v = (va | vb) | (vc | vd);
         } else {
 #pragma unroll
           for (int d = -r; d <= r; ++d) v |= bits[reflect_idx(i + d, Wy) * words + w];
@@ -501,12 +576,8 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
       {   // warp-aggregated append of the active tiles of this step
         const bool act = (i < Wy && w < words) && dl != 0u;
         const unsigned am = __ballot_sync(FULL, act);
-        if (am) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(&counter[0], __popc(am));
-          base = __shfl_sync(FULL, base, 0);
-          if (act) tiles[base + __popc(am & ((1u << lane) - 1u))] = (unsigned)(i * words + w);
-        }
+        if (act) myTiles[myCount + __popc(am & ((1u << lane) - 1u))] = (unsigned short)(i * words + w);
+        myCount += __popc(am);
       }
     }
   } else {
@@ -525,7 +596,13 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
       if (valid < 32) dl &= valid <= 0 ? 0u : ((1u << valid) - 1u);
       dil[t] = dl;
       myActive += __popc(dl);
-      if (dl != 0u) tiles[atomicAdd(&counter[0], 1)] = (unsigned)t;
+    }
+    for (int t0 = warp * 32; t0 < Wy * words; t0 += NTC) {     // same words, warp-aggregated append
+      const int t = t0 + lane;
+      const bool act = t < Wy * words && dil[t] != 0u;
+      const unsigned am = __ballot_sync(FULL, act);
+      if (act) myTiles[myCount + __popc(am & ((1u << lane) - 1u))] = (unsigned short)t;
+      myCount += __popc(am);
     }
   }
 #pragma unroll
@@ -534,6 +611,7 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
   csync();
   int nActive = 0;
   for (int w2 = 0; w2 < NWC; ++w2) nActive += s_active[w2];
+  sc.mark(4);      // D1 dilation + tile list
   // probMin (:43): every blurred value is >= the all-background value B2 (each operation is monotone in its inputs
   // and the background has the lowest inputs), so as soon as one inactive cell exists probMin == B2 and the clamp
   // threshold is known before the blur; otherwise the caller takes the minimum and clamps afterwards.
@@ -544,21 +622,110 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
   //     First pass (axis 0) depends only on the 2r+1 occupancy bits of a column:
   //       out = x[c]*w[r]; out += (x[c+j] + x[c-j])*w[j+r], j = -r..-1, with x in {log(missProb), 0}.
   double mn = 0.0;
-  const int nTiles = Wy * words;
-  double* Vw = VwAll + warp * (TPI * 64);
+  double* Vw = VwAll + warp * VW_PER_WARP;
+  if (RT > 0) {
+    // TG tiles per warp iteration.  All 2*TG first-pass patterns / table look-ups of a lane are in flight together;
+    // the second pass maps 8 lanes x 4 adjacent cells onto each tile, so a lane reads its 4 + 2r first-pass values
+    // with 16-byte loads and keeps the taps in registers.
+    constexpr int VS = 32 + 2 * (RT ? RT : 1), NV = 4 + 2 * (RT ? RT : 1), R = RT ? RT : 1;
+    double wreg[R + 1];
+#pragma unroll
+    for (int jj = 0; jj <= R; ++jj) wreg[jj] = s_w[jj];
+    const int u2 = lane >> 3, q4 = (lane & 7) * 4;
+    const unsigned patMask = (2u << (2 * R)) - 1u;
+    const unsigned wordsMagic = (unsigned)((0x100000000ull + (unsigned)words - 1) / (unsigned)words);   // ceil(2^32 / words)
+    const int nList = myCount;
+    __syncwarp();
+    for (int base = 0; base < nList; base += TG) {
+      int ti[TG], tw[TG];
+      unsigned dls[TG];
+#pragma unroll
+      for (int u = 0; u < TG; ++u) {
+        const int tt = base + u < nList ? (int)myTiles[base + u] : -1;
+        dls[u] = tt >= 0 ? dil[tt] : 0u;
+        ti[u] = tt < 0 ? 0 : (int)__umulhi((unsigned)tt, wordsMagic);      // tt / words (tt < 2^16: exact)
+        tw[u] = tt < 0 ? 0 : tt - ti[u] * words;
+      }
+      // virtual columns 32w-r .. 32w+31+r of every tile: lane handles vc0 = 32w-r+lane and (lane < 2r) vc1 = vc0+32
+      unsigned sr[TG][2];
+#pragma unroll
+      for (int u = 0; u < TG; ++u) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = ti[u];
+          const int col = reflect_idx(32 * tw[u] - R + lane + 32 * h, Wx);
+          const unsigned* colBits = bitsT + col * WT;
+          unsigned pat;
+          if (i - R >= 0 && i + R < Wy) {       // the column's 2r+1 rows straight out of the transposed bitmap
+            const int lo = i - R;
+            pat = __funnelshift_r(colBits[lo >> 5], colBits[(lo >> 5) + 1], lo & 31) & patMask;
+          } else {                              // top / bottom border: reflected rows, bit by bit
+            pat = 0u;
+            for (int d = -R; d <= R; ++d) {
+              const int rr = reflect_idx(i + d, Wy);
+              pat |= ((colBits[rr >> 5] >> (rr & 31)) & 1u) << (d + R);
+            }
+          }
+          sr[u][h] = pat;
+        }
+      }
+      double vv[TG][2];
+#pragma unroll
+      for (int u = 0; u < TG; ++u) {
+        vv[u][0] = __ldg(lut + sr[u][0]);       // first-pass value of this column pattern
+        vv[u][1] = __ldg(lut + sr[u][1]);
+      }
+#pragma unroll
+      for (int u = 0; u < TG; ++u) {
+        Vw[u * VS + lane] = vv[u][0];
+        if (lane < 2 * R) Vw[u * VS + lane + 32] = vv[u][1];
+      }
+      __syncwarp();
+      // second pass (axis 1): lane (u2, q4) owns cells 32w + q4 .. q4+3 of tile u2
+      const unsigned dsel = u2 == 0 ? dls[0] : (u2 == 1 ? dls[1] : (u2 == 2 ? dls[2] : dls[3]));
+      const int tisel = u2 == 0 ? ti[0] : (u2 == 1 ? ti[1] : (u2 == 2 ? ti[2] : ti[3]));
+      const int twsel = u2 == 0 ? tw[0] : (u2 == 1 ? tw[1] : (u2 == 2 ? tw[2] : tw[3]));
+      const unsigned act4 = (dsel >> q4) & 0xfu;
+      if (act4) {
+        double c[NV];
+        const double2* c2 = reinterpret_cast<const double2*>(Vw + u2 * VS + q4);
+#pragma unroll
+        for (int m = 0; m < NV / 2; ++m) {
+          const double2 t2 = c2[m];
+          c[2 * m] = t2.x; c[2 * m + 1] = t2.y;
+        }
+        double* out = Pf + (size_t)tisel * Pp + 32 * twsel + q4;
+        double val[4];                                  // four independent dependency chains interleave
+#pragma unroll
+        for (int e = 0; e < 4; ++e) val[e] = dmul(c[e + R], wreg[R]);
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) val[e] = dadd(val[e], dmul(dadd(c[e + jj], c[e + 2 * R - jj]), wreg[jj]));
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if ((act4 >> e) & 1u) {
+            mn = fmin(mn, val[e]);
+            out[e] = val[e] > thr ? 0.0 : val[e];       // clamp (:44)
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    const int nTiles = Wy * words;
+    (void)nTiles;
   const unsigned patMask = (2u << (2 * r)) - 1u;
-  const int nList = counter[0];
-  for (;;) {
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&counter[1], TPI);
-    base = __shfl_sync(FULL, base, 0);
-    if (base >= nList) break;
+  const int nList = myCount;
+  __syncwarp();
+  for (int base = 0; base < nList; base += TPI) {
     {
       int tt[TPI];
       unsigned dls[TPI];
 #pragma unroll
       for (int u = 0; u < TPI; ++u) {
-        tt[u] = base + u < nList ? (int)tiles[base + u] : -1;
+        tt[u] = base + u < nList ? (int)myTiles[base + u] : -1;
         dls[u] = tt[u] >= 0 ? dil[tt[u]] : 0u;
       }
       int ti[TPI], tw[TPI];
@@ -606,6 +773,8 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
       __syncwarp();
     }
   }
+  }
+  sc.mark(5);      // D2 (own tiles; the wait for the other warps is accounted to the caller)
   mnOut = mn;
   activeOut = nActive;
   thrOut = anyInactive ? thr : 0.0;     // 0.0 = "not clamped yet"
@@ -620,35 +789,49 @@ struct ScoreArgs {
   size_t gP, gDil, gScores;
   int oLists, oCnt, oP, oDil, oScores, needScores;
   int Kpad, Pp, words, nHalf, nOff, nt, t0;
+  unsigned bestS;       // shared address of the branch-and-bound incumbent (fine stage)
+  double* bestP;        // the same as a pointer
 };
 
 // Score volume of a batch of thetas (phase G2).  Kept out of line so the hot gather loop gets its own register
 // allocation instead of inheriting the pressure of the rest of the fused kernel.
-template <bool FAST, bool DENSE>
+template <bool FAST, bool DENSE, bool PRUNE>
 __device__ __noinline__ void score_batch(const ScoreArgs& A, double& bestIO, int& bestIdxIO, int& nanIO) {
   const unsigned* lists = sbuf<unsigned>(A.oLists);
   const int* cnts = sbuf<int>(A.oCnt);
   const double* Pf = DENSE ? sbuf<double>(A.oP) : reinterpret_cast<const double*>(A.gslot + A.gP);
   const unsigned* dil = buf<FAST, unsigned>(A.oDil, A.gslot, A.gDil);
   double* scores = A.needScores ? buf<FAST, double>(A.oScores, A.gslot, A.gScores) : nullptr;
-  const int tid = threadIdx.x;
+  const int tid = ctid();
   const int nOff = A.nOff, nOff2 = nOff * nOff;
   const int nGrp = (nOff + GRP - 1) / GRP;
   const int perTheta = nOff * nGrp;
   const int nq = A.nt * perTheta;
   double best = bestIO;
   int bestIdx = bestIdxIO, sawNan = nanIO;
+  PruneCtx pc;
+  pc.bestS = A.bestS; pc.h1 = 0; pc.validMask = 0;
+#pragma unroll
+  for (int g = 0; g < GRP; ++g) pc.a1[g] = 0.0;
   for (int q = tid; q < nq; q += NTC) {
-    const int tl = q / perTheta, rem0 = q - tl * perTheta;
+    int tl = q / perTheta;
+    const int rem0 = q - tl * perTheta;
+    if (PRUNE) {      // most promising rotations first (centre of the batch outwards): good incumbents early
+      const int mid = A.nt >> 1;
+      tl = (tl & 1) ? mid + ((tl + 1) >> 1) : mid - (tl >> 1);
+      if (tl >= A.nt) tl = A.nt - 1 - (tl - A.nt);      // (only when nt is even: fold the overshoot back)
+      if (tl < 0) tl = 0;
+    }
     const int a = rem0 / nGrp, b0 = (rem0 - a * nGrp) * GRP;
     double sc[GRP];
+    bool pruned = false;
     if (DENSE) {
       FetchDense f;
       f.listS = smem_u32(lists + tl * A.Kpad);
       f.baseS = smem_u32(Pf);
       f.off = (unsigned)(((b0 - A.nHalf) << 16) + (a - A.nHalf));
       f.pitch = A.Pp;
-      pairwise_g(f, cnts[tl], sc);                                 // np.sum(axis=2) :130
+      pairwise_g<false>(f, cnts[tl], sc, pc);                      // np.sum(axis=2) :130
     } else {
       FetchGated<FAST> f;
       f.list = lists + tl * A.Kpad;
@@ -657,8 +840,10 @@ __device__ __noinline__ void score_batch(const ScoreArgs& A, double& bestIO, int
       f.dilS = FAST ? smem_u32(dil) : 0u;
       f.P = Pf; f.B2 = A.B2; f.pitch = A.Pp; f.words = A.words;
       f.off = (unsigned)(((b0 - A.nHalf) << 16) + (a - A.nHalf));
-      pairwise_g(f, cnts[tl], sc);
+      pc.validMask = (b0 + 1 < nOff) ? 3 : 1;
+      pruned = pairwise_g<PRUNE>(f, cnts[tl], sc, pc);
     }
+    if (pruned) continue;
 #pragma unroll
     for (int g = 0; g < GRP; ++g) {
       const int b = b0 + g;
@@ -672,6 +857,10 @@ __device__ __noinline__ void score_batch(const ScoreArgs& A, double& bestIO, int
         if (A.dvol) A.dvol[flat] = v;
         if (v != v) sawNan = 1;
         if (bestIdx < 0 || v > best || (v == best && flat < bestIdx)) { best = v; bestIdx = flat; }
+        if (PRUNE && v > lds_f64(A.bestS)) {
+          // scores are <= 0: the larger double has the smaller bit pattern
+          atomicMin(reinterpret_cast<unsigned long long*>(A.bestP), (unsigned long long)__double_as_longlong(v));
+        }
       }
     }
   }
@@ -691,7 +880,7 @@ __device__ __noinline__ void lists_batch(const ListArgs& A, int& statusIO) {
   const double* dys = sbuf<double>(A.oDy);
   unsigned* lists = sbuf<unsigned>(A.oLists);
   int* cnts = sbuf<int>(A.oCnt);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = ctid() & 31, warp = ctid() >> 5;
   int status = statusIO;
   for (int tl = warp; tl < A.nt; tl += NWC)
     build_list<E>(dxs, dys, A.K0, A.ox, A.oy, A.cosT[A.t0 + tl], A.sinT[A.t0 + tl], A.bx, A.by, A.ul, A.nHalf,
@@ -726,37 +915,95 @@ struct StreamShared {
   unsigned long long uFull[2], uEmpty[2];     // union bitmap b is complete / may be overwritten
 };
 
+// One window row of a ring stage -> NTW pairs of bitmap words (plain layout: word w = cells 32w .. 32w+31 of the row).
+// All loads of the row are issued before the first ballot so that the single stream warp runs with full ILP.
+__device__ __forceinline__ float2 lds_f2(unsigned a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+// 64-cell groups per TMA box for a row of n groups: the largest divisor of n that keeps a box <= 256 cells
+__host__ __device__ constexpr int groups_per_box(int n) { return n % 4 == 0 ? 4 : (n % 3 == 0 ? 3 : (n % 2 == 0 ? 2 : 1)); }
+
+// NR window rows at a time -> bitmap words (plain layout: word w of a row = cells 32w .. 32w+31).
+// The shared-memory pipe is saturated by the compute warps' gathers and serves warps round-robin, so a stream warp
+// reads its ring at 1/16 of the pipe: every load of the batch is issued before the first ballot, lane L picks up
+// word L of the row through a 5-level select tree, and there is ONE store per row.
+template <int NTW, int NR>
+__device__ __forceinline__ void pack_rows(unsigned rowS, int rowBytes, int boxRowBytes, unsigned* Urow, int UW, int nr, int lane) {
+  constexpr int tPerBox = groups_per_box(NTW);
+  float2 lo[NR][NTW], hi[NR][NTW];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+#pragma unroll
+    for (int t = 0; t < NTW; ++t) {
+      // rows beyond the batch re-read its first row (a stage may hold a single row): never past the ring
+      const unsigned a = rowS + (unsigned)((r < nr ? r : 0) * rowBytes + (t / tPerBox) * boxRowBytes + (t % tPerBox) * 512 + lane * 8);
+      lo[r][t] = lds_f2(a);            // cell 64t + lane       (visited, total)
+      hi[r][t] = lds_f2(a + 256u);     // cell 64t + 32 + lane
+    }
+  }
+  const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8, b4 = lane & 16;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    if (r < nr) {
+      unsigned w[32];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        if (t < NTW) {
+          w[2 * t] = __ballot_sync(FULL, 2.f * lo[r][t].x > lo[r][t].y);       // visited/total > 0.5  (:29-31)
+          w[2 * t + 1] = __ballot_sync(FULL, 2.f * hi[r][t].x > hi[r][t].y);
+        } else {
+          w[2 * t] = 0u; w[2 * t + 1] = 0u;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = b0 ? w[2 * i + 1] : w[2 * i];          // lane L <- w[L]
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = b1 ? w[2 * i + 1] : w[2 * i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = b2 ? w[2 * i + 1] : w[2 * i];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) w[i] = b3 ? w[2 * i + 1] : w[2 * i];
+      const unsigned mine = b4 ? w[1] : w[0];
+      if (lane < 2 * NTW) Urow[(size_t)r * UW + lane] = mine;
+    }
+  }
+}
+
 // ---- stream warp.  For every particle of this CTA it stages the union window through a shared-memory ring with
 // TMA tensor loads (cp.async.bulk.tensor, one elected lane; RING_STAGES stages of ringRows rows in flight, no
 // registers tied up) and packs visited/total > 0.5 into the particle's union bitmap while the compute warps are
 // still busy with the previous particle.  Out-of-lattice cells arrive as zeros (not occupied).
 __device__ __noinline__ void stream_role(const MatchParams& P, const CUtensorMap* tmap, StreamShared& sh, int (*s_uwin)[4]) {
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, sw = threadIdx.x >> 5;       // stream warp sw takes the row chunks c = sw (mod NSW)
   unsigned char* gslot = P.scratch + (size_t)blockIdx.x * P.slotBytes;
   unsigned* Ubuf0 = reinterpret_cast<unsigned*>(gslot + P.gU);
-  const unsigned ring = (smem_u32(sbuf<unsigned char>(0)) + (unsigned)P.oRing + 127u) & ~127u;
   const int BY = P.ringRows, BX = P.boxCells, nB = P.nBoxes, UW = P.UW;
   const unsigned boxBytes = (unsigned)(BY * BX * 8), stageBytes = boxBytes * nB;
-  const int tPerBox = BX / 64;
+  const unsigned ring = ((smem_u32(sbuf<unsigned char>(0)) + (unsigned)P.oRing + 127u) & ~127u) + sw * RING_PER_WARP * stageBytes;
+  const int tPerBox = BX / 64, nTW = UW / 2;
   const int nMine = (P.N - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  // producer cursor (warp-uniform): particle kP, chunk cP of nChP, window wP
+  long long* cyc = (P.dbgCycles && threadIdx.x == 0) ? P.dbgCycles + (size_t)blockIdx.x * 48 : nullptr;   // [7] TMA wait, [14] pack, [15] bitmap wait
+  // producer cursor (warp-uniform): particle kP, own chunk cP (counts this warp's chunks), window wP
   int kP = 0, cP = 0, nChP = -1, wP[4] = {0, 0, 0, 0};
   unsigned issued = 0, consumed = 0;
+  auto my_chunks = [&](int rows) { const int n = (rows + BY - 1) / BY; return n > sw ? (n - sw + NSW - 1) / NSW : 0; };
   auto top_up = [&]() {
-    while (issued - consumed < (unsigned)RING_STAGES && kP < nMine) {
+    while (issued - consumed < (unsigned)RING_PER_WARP && kP < nMine) {
       const int pP = (int)blockIdx.x + kP * (int)gridDim.x;
       if (nChP < 0) {
         union_window(P, pP, wP);
-        nChP = (wP[2] + BY - 1) / BY;
+        nChP = my_chunks(wP[2]);
         cP = 0;
       }
       if (cP >= nChP) { ++kP; nChP = -1; continue; }
-      const unsigned st = issued % RING_STAGES;
+      const unsigned st = issued % RING_PER_WARP;
       if (lane == 0) {
-        const unsigned bar = smem_u32(&sh.ringFull[st]);
+        const unsigned bar = smem_u32(&sh.ringFull[sw * RING_PER_WARP + st]);
         mbar_expect_tx(bar, stageBytes);
         for (int j = 0; j < nB; ++j)
-          tma_load_3d(ring + st * stageBytes + j * boxBytes, tmap, bar, wP[1] + j * BX, wP[0] + cP * BY, pP);
+          tma_load_3d(ring + st * stageBytes + j * boxBytes, tmap, bar, wP[1] + j * BX, wP[0] + (sw + cP * NSW) * BY, pP);
       }
       ++issued; ++cP;
     }
@@ -765,42 +1012,45 @@ __device__ __noinline__ void stream_role(const MatchParams& P, const CUtensorMap
     const int p = (int)blockIdx.x + k * (int)gridDim.x, b = k & 1;
     int w[4];
     union_window(P, p, w);
-    const int nCh = (w[2] + BY - 1) / BY;
+    const int nCh = my_chunks(w[2]);
     unsigned* U = Ubuf0 + (size_t)b * P.URows * UW;
     top_up();                                                     // loads of this (and the next) particle in flight
+    if (cyc) cyc[15] -= clock64();
     mbar_wait(smem_u32(&sh.uEmpty[b]), (unsigned)(((k >> 1) & 1) ^ 1));   // compute is done with bitmap b
-    if (lane < 4) s_uwin[b][lane] = w[lane];
+    if (cyc) cyc[15] += clock64();
+    if (sw == 0 && lane < 4) s_uwin[b][lane] = w[lane];
     for (int c = 0; c < nCh; ++c) {
-      const unsigned st = consumed % RING_STAGES;
-      mbar_wait(smem_u32(&sh.ringFull[st]), (consumed / RING_STAGES) & 1u);
+      const unsigned st = consumed % RING_PER_WARP;
+      if (cyc) cyc[7] -= clock64();
+      mbar_wait(smem_u32(&sh.ringFull[sw * RING_PER_WARP + st]), (consumed / RING_PER_WARP) & 1u);
+      if (cyc) { const long long t = clock64(); cyc[7] += t; cyc[14] -= t; }
       const unsigned stage = ring + st * stageBytes;
-      for (int r = 0; r < BY; ++r) {
-        const int row = c * BY + r;
+      for (int r = 0; r < BY; r += 2) {            // two rows per batch (a stage row pitch inside a box is BX cells)
+        const int row = (sw + c * NSW) * BY + r;
         if (row >= w[2]) break;
-        unsigned mine = 0u;
-        int t = 0;
-        for (int j = 0; j < nB; ++j) {
-          const unsigned rowS = stage + (unsigned)(((j * BY + r) * BX + 2 * lane) * 8);
-          for (int tt = 0; tt < tPerBox; ++tt, ++t) {
-            float4 v;
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(rowS + 512u * tt));
-            const unsigned we = __ballot_sync(FULL, 2.f * v.x > v.y);   // cells 64t + 2*lane      (:29-31)
-            const unsigned wo = __ballot_sync(FULL, 2.f * v.z > v.w);   // cells 64t + 2*lane + 1
-            if (lane == ((2 * t) & 31)) mine = we;
-            if (lane == ((2 * t + 1) & 31)) mine = wo;
-            if (((2 * t + 1) & 31) == 31 || (j == nB - 1 && tt == tPerBox - 1)) {
-              const int idx = ((2 * t + 1) & ~31) + lane;
-              if (idx <= 2 * t + 1 && idx < UW) U[(size_t)row * UW + idx] = mine;
-              mine = 0u;
-            }
-          }
+        const int nr = min(min(2, BY - r), w[2] - row);
+        const unsigned rowS = stage + (unsigned)(r * BX * 8);
+        unsigned* Urow = U + (size_t)row * UW;
+        switch (nTW) {      // 64-cell groups per row: compile-time trip counts for the common window sizes
+          case 4: pack_rows<4, 2>(rowS, BX * 8, (int)boxBytes, Urow, UW, nr, lane); break;
+          case 5: pack_rows<5, 2>(rowS, BX * 8, (int)boxBytes, Urow, UW, nr, lane); break;
+          case 6: pack_rows<6, 2>(rowS, BX * 8, (int)boxBytes, Urow, UW, nr, lane); break;
+          case 8: pack_rows<8, 2>(rowS, BX * 8, (int)boxBytes, Urow, UW, nr, lane); break;
+          case 9: pack_rows<9, 2>(rowS, BX * 8, (int)boxBytes, Urow, UW, nr, lane); break;
+          case 10: pack_rows<10, 2>(rowS, BX * 8, (int)boxBytes, Urow, UW, nr, lane); break;
+          default:
+            for (int rr = 0; rr < nr; ++rr)
+              for (int t = 0; t < nTW; ++t)
+                pack_rows<1, 1>(rowS + (unsigned)(rr * BX * 8 + (t / tPerBox) * (int)boxBytes + (t % tPerBox) * 512), 0, 0,
+                                Urow + (size_t)rr * UW + 2 * t, UW, 1, lane);
         }
       }
       __syncwarp();
+      if (cyc) cyc[14] += clock64();
       ++consumed;
       top_up();                                                   // refill the stage just drained
     }
-    mbar_arrive(smem_u32(&sh.uFull[b]));                          // all 32 lanes: their bitmap words are published
+    mbar_arrive(smem_u32(&sh.uFull[b]));                          // 32 * NSW arrivals: every lane's bitmap words are published
   }
 }
 
@@ -813,7 +1063,7 @@ template <bool FAST, bool DENSE>
 __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, int p, double cx, double cy, double cth,
                           bool sample, double uniform, unsigned char* gslot, BlockScratch& bs, int& status,
                           StageOut& out, long long* cyc, const unsigned* U, const int* uwin, unsigned uEmptyBar) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = ctid(), lane = tid & 31, warp = tid >> 5;
   const double ul = S.unitLength;
   const int r = S.r;
 
@@ -843,84 +1093,241 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
 
   csync();  // previous users of the arena are done
   if (cyc && tid == 0) cyc[0] -= clock64();
+  long long* sub = cyc ? cyc + (stageId == 0 ? 16 : 32) - (stageId == 0 ? 0 : 8) : nullptr;   // cyc is already offset by 8 for stage 1
+  SubCyc sc;
+  sc.start(sub);
 
-  // ---- B. clear bitmap, float64 index maps (:36 via :173-176) -- rows of OccupancyGridX are identical
+  // ---- B. clear bitmaps, float64 index maps (:36 via :173-176) -- rows of OccupancyGridX are identical -- and the
+  //         statistics of the maps that select the scatter path
+  int* stat = bs.ibcast;            // [0] min, [1] max of colMap[j] - j; [2], [3] same for rows; [4] "not monotone"
+  if (tid == 0) { stat[0] = 1 << 30; stat[1] = -(1 << 30); stat[2] = 1 << 30; stat[3] = -(1 << 30); stat[4] = 0; }
   for (int i = tid; i < Wy * words; i += NTC) bits[i] = 0u;
   for (int i = tid; i < Wx * WT; i += NTC) bitsT[i] = 0u;
   if (dense)
     for (int i = tid; i < Wy * Pp; i += NTC) Pf[i] = S.B2;
-  for (int j = tid; j < ncols; j += NTC) {
-    int c = (int)ddiv(dsub(P.gridX[mx0 + j], xr0), ul);
-    if (c < 0 || c >= Wx) { status |= SLAM_ST_INDEX_OUT_OF_FIELD; c = min(max(c, 0), Wx - 1); }
-    colMap[j] = (short)c;
-  }
-  for (int i = tid; i < nrows; i += NTC) {
-    int c = (int)ddiv(dsub(P.gridY[my0 + i], yr0), ul);
-    if (c < 0 || c >= Wy) { status |= SLAM_ST_INDEX_OUT_OF_FIELD; c = min(max(c, 0), Wy - 1); }
-    rowMap[i] = (short)c;
+  csync();
+  {
+    int mn = 1 << 30, mx = -(1 << 30);
+    for (int j = tid; j < ncols; j += NTC) {
+      int c = (int)ddiv(dsub(P.gridX[mx0 + j], xr0), ul);
+      if (c < 0 || c >= Wx) { status |= SLAM_ST_INDEX_OUT_OF_FIELD; c = min(max(c, 0), Wx - 1); }
+      colMap[j] = (short)c;
+      mn = min(mn, c - j); mx = max(mx, c - j);
+    }
+    mn = __reduce_min_sync(FULL, mn); mx = __reduce_max_sync(FULL, mx);
+    if (lane == 0 && mn <= mx) { atomicMin(&stat[0], mn); atomicMax(&stat[1], mx); }
+    mn = 1 << 30; mx = -(1 << 30);
+    for (int i = tid; i < nrows; i += NTC) {
+      int c = (int)ddiv(dsub(P.gridY[my0 + i], yr0), ul);
+      if (c < 0 || c >= Wy) { status |= SLAM_ST_INDEX_OUT_OF_FIELD; c = min(max(c, 0), Wy - 1); }
+      rowMap[i] = (short)c;
+      mn = min(mn, c - i); mx = max(mx, c - i);
+    }
+    mn = __reduce_min_sync(FULL, mn); mx = __reduce_max_sync(FULL, mx);
+    if (lane == 0 && mn <= mx) { atomicMin(&stat[2], mn); atomicMax(&stat[3], mx); }
   }
   csync();
+  sc.mark(0);      // B clear + maps
 
-  // ---- C. scatter the occupied cells of this stage's window (:29-37) out of the particle's union bitmap, which the
-  //         streaming warp built in the background (bit planes: word 2t = cells 64t+2l, word 2t+1 = cells 64t+2l+1).
+  // ---- C. occupied cells of this stage's window (:29-37) out of the particle's union bitmap (plain layout: word w of
+  //         a row = cells 32w .. 32w+31), which the stream warp built in the background.  Three paths, same result:
+  //   shift   both index maps are "j + D or j + D - 1" (fine stage: map and field share the lattice, truncation
+  //           noise decides): whole words move -- masked funnel shifts, OR of the <= 2 source rows; no atomics
+  //   range   monotone many-to-one maps (coarse stage): OR of the source-row range, then one bit-range test per cell
+  //   generic one atomicOr per occupied cell (any map)
   {
     const int uy0 = uwin[0], ux0 = uwin[1], unr = uwin[2], unc = uwin[3];
     if (my0 < uy0 || my1 > uy0 + unr || mx0 < ux0 || mx1 > ux0 + unc) {
       if (nrows > 0 && ncols > 0) status |= SLAM_ST_WINDOW_OUTSIDE_MAP;     // union window was clipped
     }
     const int UW = P.UW;
-    const int wlo = ((mx0 - ux0) >> 6) * 2, whi = min((((mx1 - 1 - ux0) >> 6) + 1) * 2, UW);
-    const int nw = max(whi - wlo, 0);
-    const int rlo = max(my0 - uy0, 0), rhi = min(my1 - uy0, unr);
-    const int total = max(rhi - rlo, 0) * nw;
-    // a warp takes 32 bitmap words at a time and spreads their set bits evenly over its lanes: lane j handles the
-    // j-th set bit of the group (owner word by binary search over the popcount prefix, bit by __fns)
-    auto loadw = [&](int base) -> unsigned {
-      const int idx = base + lane;
-      if (idx >= total) return 0u;
-      const int rr = idx / nw;
-      return __ldcg(U + (size_t)(rlo + rr) * UW + wlo + (idx - rr * nw));
-    };
-    unsigned wnext = loadw(warp * 32);
-    for (int base = warp * 32; base < total; base += NWC * 32) {
-      const unsigned wmine = wnext;
-      wnext = loadw(base + NWC * 32);                    // next group's words are in flight while this one is expanded
-      const int cnt = __popc(wmine);
-      int incl = cnt;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(FULL, incl, d);
-        if (lane >= d) incl += t;
+    const int ax = mx0 - ux0, ay = my0 - uy0;          // window origin inside the union bitmap
+    const int Dc = stat[1], Dr = stat[3];
+    int mode = 0;
+    if (ncols > 0 && nrows > 0 && ax >= 0 && ay >= 0 && !P.forceGenericScatter) {
+      if (UW <= 32 && words <= 32 && Dc - stat[0] <= 1 && Dr - stat[2] <= 1) mode = 1;
+      else if (S.auxOK && UW <= 64) mode = 2;
+    }
+    short* colLo = sbuf<short>(S.oAux);
+    short* colHi = colLo + S.auxPitch;
+    short* rowLo = colHi + S.auxPitch;
+    short* rowHi = rowLo + S.auxPitch;
+    unsigned* rowbuf = reinterpret_cast<unsigned*>(rowHi + S.auxPitch);     // [Wy][UW]
+    if (mode == 2) {      // source ranges of every field column / row; falls back if a map is not monotone
+      for (int i = tid; i < S.auxPitch; i += NTC) { colLo[i] = 0; colHi[i] = 0; rowLo[i] = 0; rowHi[i] = 0; }
+      csync();
+      int bad = 0;
+      for (int j = tid; j < ncols; j += NTC) {
+        const int c = colMap[j], pv = j > 0 ? (int)colMap[j - 1] : -1, nx = j + 1 < ncols ? (int)colMap[j + 1] : 1 << 20;
+        if (c < pv) bad = 1;
+        if (c != pv) colLo[c] = (short)j;
+        if (c != nx) colHi[c] = (short)(j + 1);
       }
-      const int tot = __shfl_sync(FULL, incl, 31);
-      const int excl = incl - cnt;
-      for (int j0 = 0; j0 < tot; j0 += 32) {
-        const int j = min(j0 + lane, tot - 1);
-        int L = 0;
+      for (int i = tid; i < nrows; i += NTC) {
+        const int c = rowMap[i], pv = i > 0 ? (int)rowMap[i - 1] : -1, nx = i + 1 < nrows ? (int)rowMap[i + 1] : 1 << 20;
+        if (c < pv) bad = 1;
+        if (c != pv) rowLo[c] = (short)i;
+        if (c != nx) rowHi[c] = (short)(i + 1);
+      }
+      csync();
+      for (int c = tid; c < Wx; c += NTC)
+        if (colHi[c] - colLo[c] > 32) bad = 1;
+      for (int c = tid; c < Wy; c += NTC)
+        if (rowHi[c] - rowLo[c] > 32) bad = 1;
+      if (bad) stat[4] = 1;
+      csync();
+      if (stat[4]) mode = 0;
+    }
+    if (mode == 1) {
+      // masks: bit k of word t <=> union column 32t + k is window column j = 32t + k - ax with colMap[j] - j == Dc (A) / Dc - 1 (B)
+      for (int t = warp; t < UW; t += NWC) {
+        const int j = 32 * t + lane - ax;
+        const bool in = j >= 0 && j < ncols;
+        const int off = in ? (int)colMap[j] - j : 0;
+        const unsigned mA = __ballot_sync(FULL, in && off == Dc), mB = __ballot_sync(FULL, in && off == Dc - 1);
+        if (lane == 0) { bs.maskA[t] = mA; bs.maskB[t] = mB; }
+      }
+      csync();
+      const int sA = Dc - ax;                          // field column = union column + sA (A) / + sA - 1 (B)
+      const unsigned mA = lane < UW ? bs.maskA[lane] : 0u, mB = lane < UW ? bs.maskB[lane] : 0u;
+      constexpr int RU4 = 12;                          // field rows per warp iteration: independent L2 load chains
+      for (int fr0 = warp * RU4; fr0 < Wy; fr0 += NWC * RU4) {
+        unsigned x[RU4];
 #pragma unroll
-        for (int step = 16; step >= 1; step >>= 1) {
-          const int probe = __shfl_sync(FULL, incl, L + step - 1);
-          if (probe <= j) L += step;
+        for (int q = 0; q < RU4; ++q) {
+          const int fr = fr0 + q;
+          const int i1 = fr - Dr, i2 = i1 + 1;         // the <= 2 window rows that map onto field row fr
+          const bool v1 = fr < Wy && i1 >= 0 && i1 < nrows && rowMap[i1] == fr && i1 + ay < unr;
+          const bool v2 = fr < Wy && i2 >= 0 && i2 < nrows && rowMap[i2] == fr && i2 + ay < unr;
+          unsigned xa = 0u, xb = 0u;
+          if (lane < UW) {
+            if (v1) xa = __ldcg(U + (size_t)(i1 + ay) * UW + lane);
+            if (v2) xb = __ldcg(U + (size_t)(i2 + ay) * UW + lane);
+          }
+          x[q] = xa | xb;
         }
-        const unsigned wv = __shfl_sync(FULL, wmine, L);
-        const int kth = j - __shfl_sync(FULL, excl, L);
-        if (j0 + lane < tot) {
-          const int bit = __fns(wv, 0, kth + 1);
-          const int id2 = base + L;
-          const int rr = id2 / nw, wi = wlo + (id2 - rr * nw);
-          const int i = uy0 + rlo + rr - my0;                               // window row
-          const int jc = ((wi >> 1) << 6) + (wi & 1) + 2 * bit + ux0 - mx0;   // window column
-          if (jc >= 0 && jc < ncols) {
-            const int fr = (int)rowMap[i];
-            const int c = colMap[jc];
-            atomicOr(&bits[fr * words + (c >> 5)], 1u << (c & 31));
-            atomicOr(&bitsT[c * WT + (fr >> 5)], 1u << (fr & 31));
+        const int baseA = 32 * lane - sA, baseB = baseA + 1;
+        const int tA = baseA >> 5, tB = baseB >> 5;
+        const bool okA0 = tA >= 0 && tA <= 31, okA1 = tA + 1 >= 0 && tA + 1 <= 31;
+        const bool okB0 = tB >= 0 && tB <= 31, okB1 = tB + 1 >= 0 && tB + 1 <= 31;
+#pragma unroll
+        for (int q = 0; q < RU4; ++q) {
+          const unsigned a = x[q] & mA, b = x[q] & mB;
+          unsigned loA = __shfl_sync(FULL, a, tA & 31), hiA = __shfl_sync(FULL, a, (tA + 1) & 31);
+          unsigned loB = __shfl_sync(FULL, b, tB & 31), hiB = __shfl_sync(FULL, b, (tB + 1) & 31);
+          if (!okA0) loA = 0u;
+          if (!okA1) hiA = 0u;
+          if (!okB0) loB = 0u;
+          if (!okB1) hiB = 0u;
+          const unsigned out = __funnelshift_r(loA, hiA, baseA & 31) | __funnelshift_r(loB, hiB, baseB & 31);
+          if (lane < words && fr0 + q < Wy) bits[(fr0 + q) * words + lane] = out;
+        }
+      }
+    } else if (mode == 2) {
+      for (int q = tid; q < Wy * UW; q += NTC) {       // OR of the window rows that map onto each field row
+        const int fr = q / UW, t = q - fr * UW;
+        unsigned x = 0u;
+        const int hiR = min((int)rowHi[fr], unr - ay);
+        for (int i0 = rowLo[fr]; i0 < hiR; i0 += 8) {
+          unsigned y[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] = i0 + e < hiR ? __ldcg(U + (size_t)(i0 + e + ay) * UW + t) : 0u;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x |= y[e];
+        }
+        rowbuf[q] = x;
+      }
+      csync();
+      for (int q0 = warp * 32; q0 < Wy * words * 32; q0 += NWC * 32) {     // one field cell per lane, 32 cells = 1 word
+        const int wq = q0 >> 5, fr = wq / words, g = wq - fr * words;
+        const int c = 32 * g + lane;
+        bool on = false;
+        if (c < Wx) {
+          const int lo = colLo[c] + ax, len = colHi[c] - colLo[c];
+          if (len > 0) {
+            const int t0 = lo >> 5;
+            const unsigned w0 = rowbuf[fr * UW + t0], w1 = t0 + 1 < UW ? rowbuf[fr * UW + t0 + 1] : 0u;
+            const unsigned v = __funnelshift_r(w0, w1, lo & 31);
+            on = (v & (len >= 32 ? 0xffffffffu : ((1u << len) - 1u))) != 0u;
+          }
+        }
+        const unsigned wv = __ballot_sync(FULL, on);
+        if (lane == 0) bits[fr * words + g] = wv;
+      }
+    } else {
+      const int wlo = max(ax, 0) >> 5, whi = min(((mx1 - 1 - ux0) >> 5) + 1, UW);
+      const int nw = max(whi - wlo, 0);
+      const int rlo = max(ay, 0), rhi = min(my1 - uy0, unr);
+      const int total = max(rhi - rlo, 0) * nw;
+      // a warp takes 32 bitmap words at a time and spreads their set bits evenly over its lanes: lane j handles the
+      // j-th set bit of the group (owner word by binary search over the popcount prefix, bit by __fns)
+      auto loadw = [&](int base) -> unsigned {
+        const int idx = base + lane;
+        if (idx >= total) return 0u;
+        const int rr = idx / nw;
+        return __ldcg(U + (size_t)(rlo + rr) * UW + wlo + (idx - rr * nw));
+      };
+      unsigned wnext = loadw(warp * 32);
+      for (int base = warp * 32; base < total; base += NWC * 32) {
+        const unsigned wmine = wnext;
+        wnext = loadw(base + NWC * 32);                    // next group's words are in flight while this one is expanded
+        const int cnt = __popc(wmine);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(FULL, incl, d);
+          if (lane >= d) incl += t;
+        }
+        const int tot = __shfl_sync(FULL, incl, 31);
+        const int excl = incl - cnt;
+        for (int j0 = 0; j0 < tot; j0 += 32) {
+          const int j = min(j0 + lane, tot - 1);
+          int L = 0;
+#pragma unroll
+          for (int step = 16; step >= 1; step >>= 1) {
+            const int probe = __shfl_sync(FULL, incl, L + step - 1);
+            if (probe <= j) L += step;
+          }
+          const unsigned wv = __shfl_sync(FULL, wmine, L);
+          const int kth = j - __shfl_sync(FULL, excl, L);
+          if (j0 + lane < tot) {
+            const int bit = __fns(wv, 0, kth + 1);
+            const int id2 = base + L;
+            const int rr = id2 / nw, wi = wlo + (id2 - rr * nw);
+            const int i = uy0 + rlo + rr - my0;                               // window row
+            const int jc = 32 * wi + bit - ax;                                // window column
+            if (jc >= 0 && jc < ncols) {
+              const int fr = (int)rowMap[i];
+              const int c = colMap[jc];
+              atomicOr(&bits[fr * words + (c >> 5)], 1u << (c & 31));
+              atomicOr(&bitsT[c * WT + (fr >> 5)], 1u << (fr & 31));
+            }
           }
         }
       }
     }
+    if (mode != 0) {      // transposed bitmap by 32x32 block transposes of the row-major one (empty blocks skipped)
+      csync();
+      sc.mark(1);    // C scatter
+      const int nrb = (Wy + 31) >> 5, nwb = (Wx + 31) >> 5;
+      for (int q = warp; q < nrb * nwb; q += NWC) {
+        const int rb = q / nwb, wb = q - rb * nwb;
+        const int row = 32 * rb + lane;
+        const unsigned w = row < Wy ? bits[row * words + wb] : 0u;
+        if (__ballot_sync(FULL, w != 0u) == 0u) continue;          // bitsT was cleared in B
+        unsigned out = 0u;
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) {
+          const unsigned m = __ballot_sync(FULL, (w >> kk) & 1u);
+          if (lane == kk) out = m;
+        }
+        const int col = 32 * wb + lane;
+        if (col < Wx) bitsT[col * WT + rb] = out;
+      }
+    }
   }
   csync();
+  sc.mark(2);      // C transposes (or the whole generic scatter)
   if (uEmptyBar && tid == 0) mbar_arrive(uEmptyBar);   // last reader of the union bitmap: the stream warp may reuse it
   if (cyc && tid == 0) { long long t = clock64(); cyc[0] += t; cyc[1] -= t; }
 
@@ -931,10 +1338,10 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
   {
     int* counter = &bs.ibcast[4];
     switch (r) {
-      case 2: blur_stage<2, FAST, DENSE>(S, gslot, Pp, Wx, Wy, counter, mn, nActive, thr); break;
-      case 4: blur_stage<4, FAST, DENSE>(S, gslot, Pp, Wx, Wy, counter, mn, nActive, thr); break;
-      case 8: blur_stage<8, FAST, DENSE>(S, gslot, Pp, Wx, Wy, counter, mn, nActive, thr); break;
-      default: blur_stage<0, FAST, DENSE>(S, gslot, Pp, Wx, Wy, counter, mn, nActive, thr); break;
+      case 2: blur_stage<2, FAST, DENSE>(S, gslot, Pp, Wx, Wy, counter, mn, nActive, thr, sub); break;
+      case 4: blur_stage<4, FAST, DENSE>(S, gslot, Pp, Wx, Wy, counter, mn, nActive, thr, sub); break;
+      case 8: blur_stage<8, FAST, DENSE>(S, gslot, Pp, Wx, Wy, counter, mn, nActive, thr, sub); break;
+      default: blur_stage<0, FAST, DENSE>(S, gslot, Pp, Wx, Wy, counter, mn, nActive, thr, sub); break;
     }
   }
   // ---- E. probMin, clamp (:43-44).  Normally done inside the blur (probMin == B2); only a window without a single
@@ -1021,6 +1428,10 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
   SA.oLists = S.oLists; SA.oCnt = S.oCnt; SA.oP = S.oP; SA.oDil = S.oDil; SA.oScores = S.oScores;
   SA.needScores = S.needScores;
   SA.Kpad = S.Kpad; SA.Pp = Pp; SA.words = words; SA.nHalf = S.nHalf; SA.nOff = nOff;
+  // exact branch-and-bound only where nothing but the argmax is needed (fine stage, no volume dump)
+  const bool prune = !DENSE && stageId == 1 && !S.needScores && !dvol && !rv && !tw && !P.noPrune;
+  SA.bestP = &bs.incumbent; SA.bestS = smem_u32(&bs.incumbent);
+  if (tid == 0) bs.incumbent = -INFINITY;
   ListArgs LA;
   LA.cosT = S.cosT; LA.sinT = S.sinT;
   LA.ox = cx; LA.oy = cy; LA.bx = xr0; LA.by = yr0; LA.ul = ul;
@@ -1035,7 +1446,8 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
     csync();
     if (cyc && tid == 0) { long long t = clock64(); cyc[3] += t; cyc[4] -= t; }
     SA.nt = nt; SA.t0 = t0;
-    score_batch<FAST, DENSE>(SA, best, bestIdx, sawNan);
+    if (prune) score_batch<FAST, DENSE, true>(SA, best, bestIdx, sawNan);
+    else score_batch<FAST, DENSE, false>(SA, best, bestIdx, sawNan);
     csync();
     if (cyc && tid == 0) cyc[4] += clock64();
   }
@@ -1170,12 +1582,12 @@ __global__ void __launch_bounds__(NT_ALL, 1) match_kernel(const __grid_constant_
   __shared__ __align__(8) StreamShared ss;
   if (threadIdx.x == 0) {
     for (int i = 0; i < RING_STAGES; ++i) mbar_init(smem_u32(&ss.ringFull[i]), 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&ss.uFull[i]), 32); mbar_init(smem_u32(&ss.uEmpty[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&ss.uFull[i]), 32 * NSW); mbar_init(smem_u32(&ss.uEmpty[i]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   // warp NWC: union-window stream (TMA producer + bit packer), runs up to one particle ahead of the compute warps
-  if (threadIdx.x >= NTC) {
+  if (threadIdx.x < 32 * NSW) {
     stream_role(P, &tmap, ss, s_uwin);
     return;
   }
@@ -1183,7 +1595,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) match_kernel(const __grid_constant_
   unsigned* Ubuf[2];
   Ubuf[0] = reinterpret_cast<unsigned*>(gslot + P.gU);
   Ubuf[1] = Ubuf[0] + (size_t)P.URows * P.UW;
-  long long* cyc = P.dbgCycles ? P.dbgCycles + (size_t)blockIdx.x * 16 : nullptr;
+  long long* cyc = P.dbgCycles ? P.dbgCycles + (size_t)blockIdx.x * 48 : nullptr;   // [0..15] phases, [16..47] sub-phases
   int k = 0;
   for (int p = blockIdx.x; p < P.N; p += gridDim.x, ++k) {
     const double x = P.estPose[3 * p], y = P.estPose[3 * p + 1], th = P.estPose[3 * p + 2];
@@ -1195,9 +1607,9 @@ __global__ void __launch_bounds__(NT_ALL, 1) match_kernel(const __grid_constant_
     const unsigned* Ucur = Ubuf[k & 1];
     const int* wcur = s_uwin[k & 1];
     const unsigned uEmpty = smem_u32(&ss.uEmpty[k & 1]);
-    if (cyc && threadIdx.x == 0) cyc[6] -= clock64();
+    if (cyc && ctid() == 0) cyc[6] -= clock64();
     mbar_wait(smem_u32(&ss.uFull[k & 1]), (unsigned)((k >> 1) & 1));   // this particle's union bitmap is complete
-    if (cyc && threadIdx.x == 0) cyc[6] += clock64();
+    if (cyc && ctid() == 0) cyc[6] += clock64();
     if (P.fast) {      // everything but the sparse fine field lives in shared memory
       run_stage<true, true>(P, P.st[0], 0, p, x, y, th, sample, u, gslot, bs, status, c, cyc, Ucur, wcur, 0u);
       run_stage<true, false>(P, P.st[1], 1, p, c.x, c.y, c.th, false, 0.0, gslot, bs, status, f, cyc2, Ucur, wcur, uEmpty);
@@ -1206,7 +1618,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) match_kernel(const __grid_constant_
       run_stage<false, false>(P, P.st[1], 1, p, c.x, c.y, c.th, false, 0.0, gslot, bs, status, f, cyc2, Ucur, wcur, uEmpty);
     }
     status = block_or(status, bs);
-    if (threadIdx.x == 0) {
+    if (ctid() == 0) {
       P.outPose[3 * p] = f.x; P.outPose[3 * p + 1] = f.y; P.outPose[3 * p + 2] = f.th;
       P.outConf[p] = c.conf;
       int* o = P.outIdx + 6 * p;
@@ -1360,11 +1772,14 @@ static int plan_stage(slam_matcher* m, const slam_geometry* g, const slam_stage_
   S.words = (S.Wmax + GRP) / 32 + 2;      // >= 1 always-zero spare word per row (two-word funnel reads)
   S.WT = (S.Wmax + 31) / 32 + 1;
   if (S.WT % 2 == 0) S.WT += 1;          // odd column pitch: conflict-free transposed-bitmap reads
+  if ((size_t)S.Wmax * S.words >= 65536) return fail(SLAM_E_UNSUPPORTED, "search window too large (16-bit tile ids)");
   S.Kpad = (g->K + 3) & ~3;
   S.E = g->K <= 256 ? 8 : 16;
   S.needScores = (stageId == 0);
   const size_t bitsBytes = (size_t)S.Wmax * S.words * 4;
   const size_t bitsTBytes = (size_t)S.Wmax * S.WT * 4;
+  S.tileCap = std::max(((S.Wmax + 2 * NW - 1) / (2 * NW) + 1) * 2 * S.words, 32 * ((S.Wmax * S.words) / NT + 2));
+  const size_t tilesBytes = align_up((size_t)NW * S.tileCap * 2, 16);
   const size_t mapBytes = align_up((size_t)S.Wmap * 2, 16);
   const size_t scoreBytes = S.needScores ? (size_t)S.nPoses * 8 : 0;
   const size_t leafBytes = S.needScores ? (size_t)S.nLeaves * 8 : 0;
@@ -1390,14 +1805,20 @@ static int plan_stage(slam_matcher* m, const slam_geometry* g, const slam_stage_
     S.oDil = S.bitsInSmem ? take(bitsBytes) : 0;      // activity bitmap lives through the correlation
     S.oDx = take(dxyBytes);
     S.oDy = take(dxyBytes);
-    S.oVw = take((size_t)NW * TPI * 64 * 8);
+    S.oVw = take((size_t)NW * VW_PER_WARP * 8);
     const size_t common = off;
     // window / blur-phase buffers
     S.oBits = S.bitsInSmem ? take(bitsBytes) : 0;
     S.oBitsT = S.bitsInSmem ? take(bitsTBytes) : 0;
     S.oRow = take(mapBytes);
     S.oCol = take(mapBytes);
-    S.oTiles = S.bitsInSmem ? take(bitsBytes) : 0;     // active-tile ids (one 32-bit id per bitmap word at most)
+    S.oTiles = S.bitsInSmem ? take(tilesBytes) : 0;    // active-tile ids: one 16-bit id per bitmap word at most, NW segments
+    {   // range-path scratch of the scatter: only when small (the coarse stage)
+      S.auxPitch = (int)align_up((size_t)std::max(S.Wmax, S.Wmap) + 8, 8);
+      const size_t auxBytes = 4 * (size_t)S.auxPitch * 2 + (size_t)S.Wmax * m->P.UW * 4;
+      S.auxOK = (auxBytes <= 16384 && off + auxBytes <= smemBudget) ? 1 : 0;
+      S.oAux = S.auxOK ? take(auxBytes) : 0;
+    }
     const size_t blurEnd = off;
     // correlate-phase buffers alias the blur-phase ones
     off = common;
@@ -1412,7 +1833,7 @@ static int plan_stage(slam_matcher* m, const slam_geometry* g, const slam_stage_
       S.gBits = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsBytes, 256);
       S.gBitsT = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsTBytes, 256);
       S.gDil = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsBytes, 256);
-      S.gTiles = g0; g0 += S.bitsInSmem ? 0 : align_up(bitsBytes, 256);
+      S.gTiles = g0; g0 += S.bitsInSmem ? 0 : align_up(tilesBytes, 256);
       S.gP = g0; g0 += S.PInSmem ? 0 : align_up(PBytes, 256);
       S.gScores = g0; g0 += (S.needScores && !S.scoresInSmem) ? align_up(scoreBytes, 256) : 0;
       slotBytes = g0;
@@ -1451,9 +1872,7 @@ extern "C" int slam_matcher_create(const slam_geometry* g, const slam_matcher_de
   P.URows = std::min((int)(2.0 * P.RU / g->unit) + 8, g->G);
   {
     const int m64 = P.UWcells / 64;
-    int dsel = 1;
-    for (int dd = 1; dd <= 4; ++dd)
-      if (m64 % dd == 0) dsel = dd;
+    const int dsel = groups_per_box(m64);
     P.boxCells = 64 * dsel;                                          // TMA box: <= 256 elements per dimension
     P.nBoxes = m64 / dsel;
   }
@@ -1463,7 +1882,8 @@ extern "C" int slam_matcher_create(const slam_geometry* g, const slam_matcher_de
     slam_matcher_destroy(m);
     return fail(SLAM_E_UNSUPPORTED, "union window row too large for the shared-memory TMA ring");
   }
-  const size_t budget = (size_t)smemMax - staticReserve - RING_STAGES * rowBytes - 128;
+  // the stage planner leaves room for two window rows per ring stage (the stream warps pack rows in pairs)
+  const size_t budget = (size_t)smemMax - staticReserve - RING_STAGES * std::min<size_t>(2 * rowBytes, 16384) - 128;
   size_t smemNeed = 0, slot = 0;
   bool fast = true;
   for (int attempt = 0; attempt < 2; ++attempt) {
@@ -1509,9 +1929,11 @@ extern "C" int slam_matcher_field_side(const slam_matcher* m, int stage) { retur
 extern "C" int slam_matcher_num_poses(const slam_matcher* m, int stage) { return m->P.st[stage & 1].nPoses; }
 
 // test / profiling hooks (not part of the reference surface)
-extern "C" void slam_matcher_set_debug(slam_matcher* m, long long* d_cycles, int forceExactCdf) {
+extern "C" void slam_matcher_set_debug(slam_matcher* m, long long* d_cycles, int flags) {
   m->P.dbgCycles = d_cycles;
-  m->P.forceExactCdf = forceExactCdf;
+  m->P.forceExactCdf = flags & 1;            // bit 0: always walk the CDF sequentially
+  m->P.forceGenericScatter = (flags >> 1) & 1;   // bit 1: always take the atomicOr scatter path
+  m->P.noPrune = (flags >> 2) & 1;               // bit 2: no branch-and-bound in the fine stage
 }
 extern "C" int slam_matcher_num_ctas(const slam_matcher* m) { return m->numCtas; }
 extern "C" int slam_matcher_plan(const slam_matcher* m, int stage, int* out8) {

@@ -221,17 +221,25 @@ extern "C" int slam_grid_init(const slam_geometry* g, float* d_grid, int32_t N, 
   return 0;
 }
 
+static size_t upd_prep_bytes(int32_t N) { return ((size_t)N * sizeof(int4) + 255) / 256 * 256; }
+
+extern "C" size_t slam_update_workspace_bytes(int32_t N) {
+  return N <= 0 ? 0 : upd_prep_bytes(N) + ((size_t)N + 1) * sizeof(int) + 256;
+}
+
 extern "C" int slam_update_grid(const slam_geometry* g, float* d_grid, int32_t N, const double* d_ranges,
-                                const double* d_pose, int32_t* d_status, void* stream) {
+                                const double* d_pose, int32_t* d_status, void* d_workspace, size_t workspaceBytes,
+                                void* stream) {
   if (!g || !d_grid || !d_ranges || !d_pose || !d_status) return fail(SLAM_E_BADARG, "slam_update_grid: null argument");
   if (N <= 0) return 0;
   if (g->K > SLAM_MAX_BEAMS) return fail(SLAM_E_UNSUPPORTED, "too many beams");
   cudaStream_t st = (cudaStream_t)stream;
-  // per-call, stream-ordered scratch on the current device (no process-global state: several grids / streams /
-  // devices may call concurrently): [N] int4 preparation records + 1 + N ints of slow-path work list
-  const size_t prepBytes = ((size_t)N * sizeof(int4) + 255) / 256 * 256;
-  unsigned char* scratch = nullptr;
-  SLAM_CUDA(cudaMallocAsync((void**)&scratch, prepBytes + ((size_t)N + 1) * sizeof(int), st));
+  // caller-provided scratch (no process-global state: several grids / streams / devices may call concurrently):
+  // [N] int4 preparation records + 1 + N ints of slow-path work list
+  if (!d_workspace || workspaceBytes < slam_update_workspace_bytes(N))
+    return fail(SLAM_E_BADARG, "slam_update_grid: workspace too small (slam_update_workspace_bytes)");
+  const size_t prepBytes = upd_prep_bytes(N);
+  unsigned char* scratch = (unsigned char*)(((size_t)d_workspace + 255) / 256 * 256);
   int4* g_prep = reinterpret_cast<int4*>(scratch);
   int* g_slow = reinterpret_cast<int*>(scratch + prepBytes);
   SLAM_CUDA(cudaMemsetAsync(g_slow, 0, sizeof(int), st));
@@ -253,6 +261,5 @@ extern "C" int slam_update_grid(const slam_geometry* g, float* d_grid, int32_t N
     update_general_kernel<<<grid, 256, 2 * g->L * sizeof(int), st>>>(P);
     SLAM_CUDA(cudaGetLastError());
   }
-  SLAM_CUDA(cudaFreeAsync(scratch, st));
   return 0;
 }

@@ -166,9 +166,10 @@ class MatcherEngine:
 
 
 def update_grids(geom, grids, n, d_ranges, d_pose, d_status):
+    ws = geom.update_workspace(n)
     with torch.cuda.device(geom.device):
         nat.check(nat.lib.slam_update_grid(geom.c, grids.data_ptr(), n, d_ranges.data_ptr(), d_pose.data_ptr(),
-                                           d_status.data_ptr(), _stream(geom.device)))
+                                           d_status.data_ptr(), ws.data_ptr(), ws.numel(), _stream(geom.device)))
 
 
 class StepResult:

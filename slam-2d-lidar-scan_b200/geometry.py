@@ -45,6 +45,7 @@ class LidarGeometry:
         self.spokesStartIdx = int(((self.numSpokes / 2 - numSamplesPerRev) / 2) % self.numSpokes)   # :30
         self._build_sector_tables()
         self.device = require_cuda(device)
+        self._updWs = {}
         dev = self.device
         self.d_gridX = torch.from_numpy(self.gridX).to(dev)
         self.d_gridY = torch.from_numpy(self.gridY).to(dev)
@@ -81,6 +82,16 @@ class LidarGeometry:
         self.localAxis = axis
         self.sector = sec.astype(np.int32)
         self.radius = np.sqrt(xg ** 2 + yg ** 2)
+
+    def update_workspace(self, n):
+        """Device scratch of slam_update_grid for n particles, one buffer per CUDA stream (grown on demand)."""
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        need = nat.lib.slam_update_workspace_bytes(n)
+        ws = self._updWs.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._updWs[key] = ws
+        return ws
 
     def mapIndex(self, x, y):
         """convertRealXYToMapIdx (OccupancyGrid.py:102-106)."""

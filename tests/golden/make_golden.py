@@ -13,6 +13,11 @@ Writes (committed, small):
     tests/golden/resample.npz          ParticleFilter.resample / weightUnbalanced known answers
     tests/golden/csail_gfs_head.json   first 20 readings of DataSet/PreprocessedData/csail_gfs (361 beams; input only)
     tests/golden/det_csail.npz         deterministic driver on the CSAIL readings, c3-like geometry, 20 frames
+  with --full (minutes of CPU):
+    tests/golden/intel_full.npz        all 910 readings of intel_gfs (raw odometry poses + ranges) and the poses of
+                                       intel_corrected_log (ground truth, same keys) as float64 arrays (input only)
+    tests/golden/det_intel_full.npz    deterministic driver over all 910 readings on pre-sized 72 m maps: reference
+                                       defaults at unit 0.02 (BASELINE.md section 2 trajectory) and c3 parameters at 0.05
 
 Nothing here is product code; the reference is only imported, never copied.
 """
@@ -180,7 +185,34 @@ def run_resample():
     return out
 
 
+def main_full():
+    """Whole-log goldens (F4 / VERDICT item 1f): poses, confidences, count sums of the deterministic driver."""
+    frames = load_frames("intel_gfs", 10 ** 6)
+    with open(os.path.join(REF, "DataSet/PreprocessedData", "intel_corrected_log")) as f:
+        gt = json.load(f)["map"]
+    assert sorted(gt.keys()) == [fr["key"] for fr in frames]
+    np.savez_compressed(
+        os.path.join(HERE, "intel_full.npz"),
+        keys=np.array([float(fr["key"]) for fr in frames]),
+        poses=np.array([[fr["x"], fr["y"], fr["theta"]] for fr in frames], dtype=np.float64),
+        ranges=np.array([fr["range"] for fr in frames], dtype=np.float64),
+        truth=np.array([[gt[fr["key"]]["x"], gt[fr["key"]]["y"], gt[fr["key"]]["theta"]] for fr in frames], dtype=np.float64))
+    init = {"x": frames[0]["x"], "y": frames[0]["y"]}
+    out = {}
+    for tag, ogArgs, smArgs in (("c3", (72, 72, init, 0.05, np.pi, 180, 10, 0.25), (1.5, 0.3, 2, 0.1, 0.25, 0.3, 0.15, 5)),
+                                ("ref02", (72, 72, init, 0.02, np.pi, 180, 10, 5 * 0.02), (1.4, 0.25, 2, 0.1, 0.25, 0.3, 0.15, 5))):
+        r = run_deterministic(frames, ogArgs, smArgs, len(frames), set())
+        out[tag + "_poses"], out[tag + "_confs"] = r["poses"], r["confs"]
+        out[tag + "_sums"] = np.array([float(r["visited"].astype(np.float64).sum()), float(r["total"].astype(np.float64).sum()),
+                                       float(len(r["cells"]))])
+        out[tag + "_sha"] = np.frombuffer(bytes.fromhex(sha(r["poses"])), dtype=np.uint8)
+        print(tag, "trajectory sha", sha(r["poses"]), "touched cells", len(r["cells"]))
+    np.savez_compressed(os.path.join(HERE, "det_intel_full.npz"), **out)
+
+
 def main():
+    if "--full" in sys.argv:
+        return main_full()
     frames = load_frames()
     with open(os.path.join(HERE, "intel_gfs_head.json"), "w") as f:
         json.dump({"source": "DataSet/PreprocessedData/intel_gfs, first %d readings (sorted keys)" % N_FRAMES,

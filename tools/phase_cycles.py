@@ -27,7 +27,7 @@ for fr in scene["warm"]:
 pf.grids.copy_(og.device_grid.unsqueeze(0).expand_as(pf.grids))
 nat = S._native
 ctas = nat.lib.slam_matcher_num_ctas(pf.engine.handle)
-cyc = torch.zeros((ctas, 16), dtype=torch.int64, device=pf.geom.device)
+cyc = torch.zeros((ctas, 48), dtype=torch.int64, device=pf.geom.device)
 plan = (nat.C.c_int * 8)()
 for s in range(2):
     nat.lib.slam_matcher_plan(pf.engine.handle, s, nat.C.byref(plan))
@@ -52,4 +52,11 @@ for st in range(2):
     for k in range(7 if st == 0 else 6):
         v = per[8 * st + k]
         print("%-7s %-12s %10.0f cycles/particle  %5.1f %%" % ("coarse" if st == 0 else "fine", names[k], v, 100 * v / tot))
+sub = ["B clear+maps", "C scatter", "C transpose", "-", "D1 dilate", "D2 blur (own tiles)"]
+for st in range(2):
+    print("  sub-phases %s: " % ("coarse" if st == 0 else "fine") + ", ".join("%s %.0f" % (sub[k], per[16 + 16 * st + k]) for k in range(6) if sub[k] != "-"))
+per[16:] = 0
+print("stream warp: TMA wait %.0f, pack %.0f, bitmap-free wait %.0f cycles/particle" % (per[7], per[14], per[15]))
+per[7] = per[14] = per[15] = 0
+tot = per.sum()
 print("total %.0f cycles/particle; status max %d" % (tot, int(pf.status.max().item())))
