@@ -39,7 +39,7 @@ constexpr int NWC = NW;          // compute warps
 constexpr int NTC = NWC * 32;    // compute threads
 constexpr int NT_ALL = 512;
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int RING_STAGES = 4;   // TMA ring depth over all stream warps (stages of ringRows window rows each)
+constexpr int RING_STAGES = NSW > 2 ? 2 * NSW : 4;   // TMA ring depth over all stream warps (stages of ringRows window rows each)
 constexpr int RING_PER_WARP = RING_STAGES / NSW;
 static_assert(RING_STAGES % NSW == 0 && RING_PER_WARP >= 1, "ring stages must split evenly over the stream warps");
 
@@ -71,8 +71,9 @@ struct StageDev {
   const double *thetas, *cosT, *sinT;
   int nLeaves;               // pairwise-sum leaves of the flattened score volume
   const int2* leaves;        // (offset, length)
-  int progLen;               // postfix combine program: >= 0 push leaf, -1 add
-  const short* prog;
+  int nOps, nLevels;         // combine tree of the leaves, ops grouped by height: node[nLeaves + o] = node[a] + node[b]
+  const int2* ops;
+  int levelStart[24];
   // ---- plan
   int Wmax, Wmap, words, WT, Ppitch, TB, Kpad, E;   // words includes >= 1 always-zero spare word per row
   int bitsInSmem, PInSmem, scoresInSmem, needScores;
@@ -537,6 +538,32 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
   int myCount = 0;
   // D1. activity bitmap: cell (i, j) is active iff an occupied cell lies within +-r rows and +-r columns
   //     (reflected taps always fall inside that span, so plain dilation is exact).
+  if (RT > 0 && words <= 32) {
+    // vertical part first, one thread per (strip of RS rows, bitmap word): the rows of the strip (+-r) are loaded once
+    // and the (2r+1)-row window OR is built by doubling in registers -- ~2 loads + 5 ORs per word instead of 2r+1 each
+    constexpr int RS = 24, W = 2 * (RT ? RT : 1) + 1, NIN = RS + W - 1;
+    constexpr int CMAX = W >= 16 ? 16 : (W >= 8 ? 8 : (W >= 4 ? 4 : (W >= 2 ? 2 : 1)));
+    const int nStrips = (Wy + RS - 1) / RS;
+    for (int u = tid; u < nStrips * words; u += NTC) {
+      const int s = u / words, w = u - s * words;
+      const int i0 = s * RS;
+      unsigned a[NIN];
+#pragma unroll
+      for (int j = 0; j < NIN; ++j) {
+        const int row = i0 - (RT ? RT : 1) + j;
+        a[j] = (row >= 0 && row < Wy) ? bits[row * words + w] : 0u;
+      }
+#pragma unroll
+      for (int c = 1; c < CMAX; c <<= 1) {
+#pragma unroll
+        for (int j = 0; j + c < NIN; ++j) a[j] |= a[j + c];      // ascending j: a[j + c] still holds the previous level
+      }
+#pragma unroll
+      for (int j = 0; j < RS; ++j)
+        if (i0 + j < Wy) dil[(i0 + j) * words + w] = a[j] | a[j + W - CMAX];
+    }
+    csync();
+  }
   if (words <= 32) {
     const int seg = words <= 16 ? 16 : 32;               // lanes per row
     const int rowsPerWarp = 32 / seg;
@@ -544,7 +571,9 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
     for (int i0 = warp * rowsPerWarp; i0 < Wy; i0 += NWC * rowsPerWarp) {
       const int i = i0 + sub;
       unsigned v = 0u;
-      if (i < Wy && w < words) {
+      if (RT > 0) {
+        if (i < Wy && w < words) v = dil[i * words + w];   // vertical window OR from the pre-pass (in place below)
+      } else if (i < Wy && w < words) {
         if (i - r >= 0 && i + r < Wy) {                  // interior: no reflection, unit-stride rows
           const unsigned* q = bits + (i - r) * words + w;
           unsigned va = 0u, vb = 0u, vc = 0u, vd = 0u;     // four OR chains instead of one
@@ -817,10 +846,8 @@ __device__ __noinline__ void score_batch(const ScoreArgs& A, double& bestIO, int
     int tl = q / perTheta;
     const int rem0 = q - tl * perTheta;
     if (PRUNE) {      // most promising rotations first (centre of the batch outwards): good incumbents early
-      const int mid = A.nt >> 1;
-      tl = (tl & 1) ? mid + ((tl + 1) >> 1) : mid - (tl >> 1);
-      if (tl >= A.nt) tl = A.nt - 1 - (tl - A.nt);      // (only when nt is even: fold the overshoot back)
-      if (tl < 0) tl = 0;
+      const int mid = A.nt >> 1;                        // bijection of [0, nt): mid, mid-1, mid+1, mid-2, ...
+      tl = (tl & 1) ? mid - 1 - (tl >> 1) : mid + (tl >> 1);
     }
     const int a = rem0 / nGrp, b0 = (rem0 - a * nGrp) * GRP;
     double sc[GRP];
@@ -926,9 +953,8 @@ __device__ __forceinline__ float2 lds_f2(unsigned a) {
 __host__ __device__ constexpr int groups_per_box(int n) { return n % 4 == 0 ? 4 : (n % 3 == 0 ? 3 : (n % 2 == 0 ? 2 : 1)); }
 
 // NR window rows at a time -> bitmap words (plain layout: word w of a row = cells 32w .. 32w+31).
-// The shared-memory pipe is saturated by the compute warps' gathers and serves warps round-robin, so a stream warp
-// reads its ring at 1/16 of the pipe: every load of the batch is issued before the first ballot, lane L picks up
-// word L of the row through a 5-level select tree, and there is ONE store per row.
+// The shared-memory pipe is shared with the compute warps' gathers and serves warps round-robin, so a stream warp
+// reads its ring at a fraction of the pipe: every load of the batch is issued before the first ballot.
 template <int NTW, int NR>
 __device__ __forceinline__ void pack_rows(unsigned rowS, int rowBytes, int boxRowBytes, unsigned* Urow, int UW, int nr, int lane) {
   constexpr int tPerBox = groups_per_box(NTW);
@@ -943,13 +969,14 @@ __device__ __forceinline__ void pack_rows(unsigned rowS, int rowBytes, int boxRo
       hi[r][t] = lds_f2(a + 256u);     // cell 64t + 32 + lane
     }
   }
-  const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8, b4 = lane & 16;
+  // every ballot is warp-uniform: lane 0 writes the row with 16-byte stores (UW is a multiple of 4 words; words past
+  // the window are zero)
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     if (r < nr) {
-      unsigned w[32];
+      unsigned w[(2 * NTW + 3) / 4 * 4];
 #pragma unroll
-      for (int t = 0; t < 16; ++t) {
+      for (int t = 0; t < (2 * NTW + 3) / 4 * 2; ++t) {
         if (t < NTW) {
           w[2 * t] = __ballot_sync(FULL, 2.f * lo[r][t].x > lo[r][t].y);       // visited/total > 0.5  (:29-31)
           w[2 * t + 1] = __ballot_sync(FULL, 2.f * hi[r][t].x > hi[r][t].y);
@@ -957,16 +984,11 @@ __device__ __forceinline__ void pack_rows(unsigned rowS, int rowBytes, int boxRo
           w[2 * t] = 0u; w[2 * t + 1] = 0u;
         }
       }
+      if (lane == 0) {
+        uint4* dst = reinterpret_cast<uint4*>(Urow + (size_t)r * UW);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) w[i] = b0 ? w[2 * i + 1] : w[2 * i];          // lane L <- w[L]
-#pragma unroll
-      for (int i = 0; i < 8; ++i) w[i] = b1 ? w[2 * i + 1] : w[2 * i];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) w[i] = b2 ? w[2 * i + 1] : w[2 * i];
-#pragma unroll
-      for (int i = 0; i < 2; ++i) w[i] = b3 ? w[2 * i + 1] : w[2 * i];
-      const unsigned mine = b4 ? w[1] : w[0];
-      if (lane < 2 * NTW) Urow[(size_t)r * UW + lane] = mine;
+        for (int g = 0; g < (2 * NTW + 3) / 4; ++g) dst[g] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+      }
     }
   }
 }
@@ -982,7 +1004,7 @@ __device__ __noinline__ void stream_role(const MatchParams& P, const CUtensorMap
   const int BY = P.ringRows, BX = P.boxCells, nB = P.nBoxes, UW = P.UW;
   const unsigned boxBytes = (unsigned)(BY * BX * 8), stageBytes = boxBytes * nB;
   const unsigned ring = ((smem_u32(sbuf<unsigned char>(0)) + (unsigned)P.oRing + 127u) & ~127u) + sw * RING_PER_WARP * stageBytes;
-  const int tPerBox = BX / 64, nTW = UW / 2;
+  const int tPerBox = BX / 64, nTW = P.UWcells / 64;
   const int nMine = (P.N - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   long long* cyc = (P.dbgCycles && threadIdx.x == 0) ? P.dbgCycles + (size_t)blockIdx.x * 48 : nullptr;   // [7] TMA wait, [14] pack, [15] bitmap wait
   // producer cursor (warp-uniform): particle kP, own chunk cP (counts this warp's chunks), window wP
@@ -1038,11 +1060,19 @@ __device__ __noinline__ void stream_role(const MatchParams& P, const CUtensorMap
           case 8: pack_rows<8, 2>(rowS, BX * 8, (int)boxBytes, Urow, UW, nr, lane); break;
           case 9: pack_rows<9, 2>(rowS, BX * 8, (int)boxBytes, Urow, UW, nr, lane); break;
           case 10: pack_rows<10, 2>(rowS, BX * 8, (int)boxBytes, Urow, UW, nr, lane); break;
-          default:
-            for (int rr = 0; rr < nr; ++rr)
-              for (int t = 0; t < nTW; ++t)
-                pack_rows<1, 1>(rowS + (unsigned)(rr * BX * 8 + (t / tPerBox) * (int)boxBytes + (t % tPerBox) * 512), 0, 0,
-                                Urow + (size_t)rr * UW + 2 * t, UW, 1, lane);
+          default:      // any other width: one 64-cell group at a time
+            for (int rr = 0; rr < nr; ++rr) {
+              for (int t = 0; t < UW / 2; ++t) {
+                unsigned w0 = 0u, w1 = 0u;
+                if (t < nTW) {
+                  const unsigned a = rowS + (unsigned)(rr * BX * 8 + (t / tPerBox) * (int)boxBytes + (t % tPerBox) * 512 + lane * 8);
+                  const float2 lo = lds_f2(a), hi = lds_f2(a + 256u);
+                  w0 = __ballot_sync(FULL, 2.f * lo.x > lo.y);
+                  w1 = __ballot_sync(FULL, 2.f * hi.x > hi.y);
+                }
+                if (lane == 0) *reinterpret_cast<uint2*>(Urow + (size_t)rr * UW + 2 * t) = make_uint2(w0, w1);
+              }
+            }
         }
       }
       __syncwarp();
@@ -1452,6 +1482,7 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
     if (cyc && tid == 0) cyc[4] += clock64();
   }
   if (cyc && tid == 0) cyc[5] -= clock64();
+  sc.start(sub);
 
   // ---- H. select (:133-141)
   if (csync_or(sawNan)) status |= SLAM_ST_NAN_SCORE;
@@ -1475,11 +1506,13 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
     chosen = bi;
     csync();
   }
+  sc.mark(8);      // H argmax
   double conf = 0.0;
   if (S.needScores) {
     const int n = S.nPoses;
     for (int i = tid; i < n; i += NTC) scores[i] = exp(scores[i]);
     csync();
+    sc.mark(9);    // H exp
     double* leafSum = sbuf<double>(S.oLeaf);
     SmemVal sv;
     sv.a = scores;
@@ -1488,26 +1521,33 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
       leafSum[l] = block_sum(sv, lf.x, lf.y);
     }
     csync();
-    if (tid == 0) {   // combine the leaves along numpy's recursion tree
-      double stack[24];
-      int sp = 0;
-      for (int i = 0; i < S.progLen; ++i) {
-        int op = S.prog[i];
-        if (op >= 0) stack[sp++] = leafSum[op];
-        else { sp--; stack[sp - 1] = dadd(stack[sp - 1], stack[sp]); }
+    if (warp == 0) {   // combine the leaves along numpy's recursion tree, one tree level at a time
+      for (int l = 0; l < S.nLevels; ++l) {
+        const int o1 = S.levelStart[l + 1];
+        for (int o = S.levelStart[l] + lane; o < o1; o += 32) {
+          const int2 op = S.ops[o];
+          leafSum[S.nLeaves + o] = dadd(leafSum[op.x], leafSum[op.y]);
+        }
+        __syncwarp();
       }
-      bs.bcast[0] = stack[0];
+      if (lane == 0) bs.bcast[0] = leafSum[S.nOps ? S.nLeaves + S.nOps - 1 : 0];     // root (a single leaf: no ops)
     }
     csync();
     conf = bs.bcast[0];
+    sc.mark(10);   // H pairwise sum of exp
     if (sample) {
       // np.random.choice: p = e / e.sum(); cdf = cumsum(p) (sequential); cdf /= cdf[-1]; searchsorted(u, 'right').
-      // Parallel prefix with a certified margin; the exact sequential walk only when u is within the rounding
-      // envelope of a CDF step (probability ~1e-10 per call).
+      // Located with a parallel prefix and certified by a margin: with p >= 0 both the sequential cumsum and the tree
+      // prefix lie within (n - 1) * 2^-53 * sum(p) of the exact prefix (Higham, Accuracy and Stability, 4.2) and the
+      // normalisation adds 2 ulp, so the two normalised CDFs differ by < (2n + 4) * 2^-53 (< 5e-12 for n <= 21870).
+      // If u is farther than tol = max(1e-10, 16 n 2^-53) from the CDF values on both sides of the located step, the
+      // exact monotone CDF crosses u at the same index; otherwise thread 0 walks the exact sequential definition.
+      for (int i = tid; i < n; i += NTC) scores[i] = ddiv(scores[i], conf);      // p = e / e.sum()
+      csync();
       const int chunk = (n + NTC - 1) / NTC;
       const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
       double part = 0.0;
-      for (int i = lo; i < hi; ++i) part += ddiv(scores[i], conf);
+      for (int i = lo; i < hi; ++i) part += scores[i];
       // block exclusive scan of the chunk sums
       double incl = part;
 #pragma unroll
@@ -1516,6 +1556,7 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
         if (lane >= d) incl += v;
       }
       if (lane == 31) bs.dval[warp] = incl;
+      if (tid == 0) { bs.ibcast[0] = -1; bs.ibcast[1] = 0; }
       csync();
       double wbase = 0.0, total = 0.0;
       for (int w2 = 0; w2 < NWC; ++w2) {
@@ -1523,16 +1564,15 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
         total += bs.dval[w2];
       }
       const double before = wbase + incl - part;
-      if (tid == 0) { bs.ibcast[0] = -1; bs.ibcast[1] = 0; }
-      csync();
-      const double tol = 1e-10;
-      if (hi > lo && before / total <= uniform && ((before + part) / total > uniform || hi == n)) {
+      const double tol = fmax(1e-10, 16.0 * (double)n * 1.1102230246251565e-16);
+      const double ut = uniform * total;
+      if (hi > lo && before <= ut && (before + part > ut || hi == n)) {
         double c = before, prev = before;
         int found = -1;
         for (int i = lo; i < hi; ++i) {
           prev = c;
-          c += ddiv(scores[i], conf);
-          if (c / total > uniform) { found = i; break; }
+          c += scores[i];
+          if (c > ut) { found = i; break; }
         }
         if (found >= 0) {
           bool amb = (uniform - prev / total) < tol || (c / total - uniform) < tol;
@@ -1548,12 +1588,12 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
       if (exact) {
         if (tid == 0) {
           double c = 0.0;
-          for (int i = 0; i < n; ++i) c = dadd(c, ddiv(scores[i], conf));
+          for (int i = 0; i < n; ++i) c = dadd(c, scores[i]);
           const double last = c;
           c = 0.0;
           int found = n;
           for (int i = 0; i < n; ++i) {
-            c = dadd(c, ddiv(scores[i], conf));
+            c = dadd(c, scores[i]);
             if (ddiv(c, last) > uniform) { found = i; break; }
           }
           bs.ibcast[0] = min(found, n - 1);
@@ -1562,6 +1602,7 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
         idx = bs.ibcast[0];
       }
       chosen = idx;
+      sc.mark(11);   // H CDF inversion
     }
   }
   if (chosen < 0) chosen = 0;
@@ -1681,17 +1722,21 @@ struct slam_matcher {
   int tmapN = 0;
 };
 
-static void leaves_rec(int off, int n, std::vector<int2>& leaves, std::vector<short>& prog) {
+// numpy's pairwise recursion over n elements: leaves (offset, length <= 128) and the internal nodes (a, b, height)
+static int leaves_rec(int off, int n, std::vector<int2>& leaves, std::vector<int3>& nodes, int& height) {
   if (n <= 128) {
-    prog.push_back((short)leaves.size());
     leaves.push_back(make_int2(off, n));
-    return;
+    height = 0;
+    return -(int)leaves.size();                 // leaf k encoded as -(k + 1)
   }
   int n2 = n / 2;
   n2 -= n2 % 8;
-  leaves_rec(off, n2, leaves, prog);
-  leaves_rec(off + n2, n - n2, leaves, prog);
-  prog.push_back(-1);
+  int ha = 0, hb = 0;
+  const int a = leaves_rec(off, n2, leaves, nodes, ha);
+  const int b = leaves_rec(off + n2, n - n2, leaves, nodes, hb);
+  height = std::max(ha, hb) + 1;
+  nodes.push_back(make_int3(a, b, height));
+  return (int)nodes.size() - 1;
 }
 
 template <class T>
@@ -1757,12 +1802,28 @@ static int plan_stage(slam_matcher* m, const slam_geometry* g, const slam_stage_
     S.lutV = (const double*)lut;
   }
   std::vector<int2> leaves;
-  std::vector<short> prog;
-  leaves_rec(0, S.nPoses, leaves, prog);
-  if (leaves.size() > 30000) return fail(SLAM_E_UNSUPPORTED, "score volume too large");
+  std::vector<int3> nodes;
+  int rootH = 0;
+  leaves_rec(0, S.nPoses, leaves, nodes, rootH);
+  if (leaves.size() > 30000 || rootH + 1 >= 24) return fail(SLAM_E_UNSUPPORTED, "score volume too large");
   S.nLeaves = (int)leaves.size();
-  S.progLen = (int)prog.size();
-  if (!S.leaves && (upload(m, leaves.data(), leaves.size(), &S.leaves) || upload(m, prog.data(), prog.size(), &S.prog)))
+  S.nOps = (int)nodes.size();
+  S.nLevels = rootH;
+  // internal nodes ordered by height (children first); ids: leaf k -> k, op o -> nLeaves + o
+  std::vector<int> order(nodes.size()), newId(nodes.size());
+  for (size_t i = 0; i < nodes.size(); ++i) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return nodes[x].z < nodes[y].z; });
+  for (size_t i = 0; i < order.size(); ++i) newId[order[i]] = (int)i;
+  std::vector<int2> ops(nodes.size());
+  for (int l = 0; l < 24; ++l) S.levelStart[l] = (int)nodes.size();
+  for (size_t i = 0; i < order.size(); ++i) {
+    const int3 nd = nodes[order[i]];
+    auto id = [&](int c) { return c < 0 ? -c - 1 : S.nLeaves + newId[c]; };
+    ops[i] = make_int2(id(nd.x), id(nd.y));
+    S.levelStart[nd.z - 1] = std::min(S.levelStart[nd.z - 1], (int)i);
+  }
+  for (int l = 22; l >= 0; --l) S.levelStart[l] = std::min(S.levelStart[l], S.levelStart[l + 1]);
+  if (!S.leaves && (upload(m, leaves.data(), leaves.size(), &S.leaves) || upload(m, ops.data(), ops.size(), &S.ops)))
     return 1;
 
   // ---- memory plan
@@ -1782,7 +1843,7 @@ static int plan_stage(slam_matcher* m, const slam_geometry* g, const slam_stage_
   const size_t tilesBytes = align_up((size_t)NW * S.tileCap * 2, 16);
   const size_t mapBytes = align_up((size_t)S.Wmap * 2, 16);
   const size_t scoreBytes = S.needScores ? (size_t)S.nPoses * 8 : 0;
-  const size_t leafBytes = S.needScores ? (size_t)S.nLeaves * 8 : 0;
+  const size_t leafBytes = S.needScores ? (size_t)(S.nLeaves + S.nOps) * 8 : 0;
   const size_t dxyBytes = align_up((size_t)g->K * 8, 16);
   // field pitch: conflict-free shared-memory gathers want pitch == nOff (mod 16) doubles
   int pp = S.Wmax;
@@ -1868,7 +1929,7 @@ extern "C" int slam_matcher_create(const slam_geometry* g, const slam_matcher_de
   const double coarseReach = d->coarse.nHalf * d->coarse.unitLength;
   P.RU = d->windowRadius + coarseReach + 2.0 * g->unit;
   P.UWcells = (((int)(2.0 * P.RU / g->unit) + 8) + 63) / 64 * 64;     // multiple of 64 cells (2 bitmap words)
-  P.UW = 2 * (P.UWcells / 64);
+  P.UW = (2 * (P.UWcells / 64) + 3) / 4 * 4;                       // bitmap words per union row: 16-byte rows
   P.URows = std::min((int)(2.0 * P.RU / g->unit) + 8, g->G);
   {
     const int m64 = P.UWcells / 64;

@@ -1,0 +1,246 @@
+"""GPU parity, second set (round-2 review items): diverged large batches against the oracle slot by slot, the CSAIL
+361-beam golden, BASELINE config-5 geometry, the global-slot (SLOW) plan in sampling mode, the FastSLAM.step facade,
+the whole 910-reading Intel log, and translation invariance.  Tolerances as in test_gpu_parity.py: poses, indices and
+map counts exact; score volumes / likelihood fields bit-exact; confidences and weights rtol 1e-12 / 1e-9 (exp)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_golden, reading, dense_counts
+from oracle import slam_oracle as O
+from test_gpu_parity import S, drive, OG_C3, SM_C3, OG_02, SM_02, CONF_RTOL, _poses   # noqa: F401  (S is a fixture)
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+
+
+def _oracle_slots(spec, scene, slots, uniforms, steps):
+    """Oracle particles for the given slots of a batched run: same pre-warmed map, slot i fed uniforms[step][i]."""
+    mapX, mapY, initXY, unit, fov, maxRange, K, wall = spec["og"]
+    geom = O.GridGeometry(mapX, mapY, initXY, unit, fov, K, maxRange, wall)
+    out = {}
+    for i in slots:
+        p = O.Particle(spec["og"], spec["sm"], geometry=geom)
+        for fr in scene["warm"]:
+            p.og.updateOccupancyGrid(fr)
+        for count, fr in enumerate(scene["frames"][:steps], start=1):
+            p.update(fr, count, uniform=None if count == 1 else float(uniforms[count][i]))
+        out[i] = p
+    return out
+
+
+def _warm(S, pf, scene):
+    og = S.OccupancyGrid(*pf.geom.args, _geometry=pf.geom)
+    for fr in scene["warm"]:
+        og.updateOccupancyGrid(fr)
+    pf.grids.copy_(og.device_grid.unsqueeze(0).expand_as(pf.grids))
+
+
+def test_diverged_1024_batch_slots_match_oracle(S):
+    """BASELINE config 3 at full size, SAMPLING mode: after 4 steps the 1024 particles have diverged; 10 scattered slots
+    (first / last of the grid-stride waves included) are compared with oracle particles fed the same uniforms."""
+    from slam_2d_lidar_scan_b200 import synthetic
+    spec = synthetic.config("c3")
+    n, steps = 1024, 4
+    scene = synthetic.make_scene(seed=0, steps=steps + 1, K=180, fov=np.pi, unit=0.05)
+    rng = np.random.RandomState(77)
+    uniforms = {c: rng.random_sample(n) for c in range(2, steps + 1)}
+    pf = S.ParticleFilter(n, spec["og"], spec["sm"])
+    _warm(S, pf, scene)
+    for count, fr in enumerate(scene["frames"][:steps], start=1):
+        pf._update(0, n, fr, count, uniforms=uniforms.get(count))
+    rawW = pf.weights.cpu().numpy().copy()
+    assert not pf.weightUnbalanced()
+    poses, idx = pf.poses(), pf._idx.cpu().numpy()
+    assert len(np.unique(poses, axis=0)) >= 8            # really diverged (the coarse softmax is peaked)
+    slots = [0, 1, 147, 148, 295, 511, 700, 887, 1022, 1023]
+    ref = _oracle_slots(spec, scene, slots, uniforms, steps)
+    for i in slots:
+        p = ref[i]
+        want = [p.prevMatchedReading[k] for k in ("x", "y", "theta")]
+        assert poses[i].tolist() == want, i
+        assert rawW[i] == pytest.approx(p.weight, rel=1e-9, abs=0)
+        g = pf.grids[i].cpu().numpy()
+        G = pf.geom.G
+        assert np.array_equal(g[:, :G, 0].astype(np.float64), p.og.occupancyGridVisited), i
+        assert np.array_equal(g[:, :G, 1].astype(np.float64), p.og.occupancyGridTotal), i
+    assert abs(pf.weights.sum().item() - 1.0) < 1e-12
+    assert (idx[:, 0] >= 0).all() and (idx[:, 0] < 36).all()
+
+
+def test_csail_361_beam_driver_matches_reference_golden(S):
+    """MIT CSAIL readings: 361 beams (numSpokes 722, 70 rotations, 512-key sorts), poses ~576 m from the origin."""
+    with open(os.path.join(GOLDEN, "csail_gfs_head.json")) as f:
+        cs = json.load(f)["frames"]
+    g = load_golden("det_csail.npz")
+    init = {"x": cs[0]["x"], "y": cs[0]["y"]}
+    grid, poses, confs, traces = drive(S, cs, (50, 50, init, 0.05, np.pi, 361, 10, 0.25), SM_C3, 20, (3, 12))
+    assert grid.geom.numSpokes == 722
+    assert np.array_equal(poses, g["poses"])
+    np.testing.assert_allclose(confs, g["confs"], rtol=CONF_RTOL, atol=0)
+    v, t = dense_counts(int(g["G"][0]), g["cells"], g["visited"], g["total"])
+    assert np.array_equal(grid.occupancyGridVisited, v) and np.array_equal(grid.occupancyGridTotal, t)
+    for c in (3, 12):
+        for stage in ("coarse", "fine"):
+            tag = "c%d_%s" % (c, stage)
+            assert np.array_equal(traces[c][stage + "_vol"], g[tag + "_vol"]), tag
+            assert np.array_equal(sha(traces[c][stage + "_prob"]), g[tag + "_prob_sha"]), tag
+
+
+def test_c5_geometry_fov_pi_360_beams_matches_oracle(S):
+    """BASELINE config 5 geometry: 360 beams over FOV pi (numSpokes 720, 70 rotations), 2001^2 lattice, sampling mode,
+    3 particles against the oracle (poses / maps exact, weights 1e-9)."""
+    from slam_2d_lidar_scan_b200 import synthetic
+    init = {"x": 0.0, "y": 0.0}
+    spec = dict(og=[100, 100, init, 0.05, np.pi, 10, 360, 0.25], sm=[1.5, 0.3, 2, 0.1, 0.25, 0.3, 0.15, 5])
+    scene = synthetic.make_scene(seed=2, steps=5, K=360, fov=np.pi, unit=0.05)
+    n, steps = 3, 4
+    rng = np.random.RandomState(5)
+    uniforms = {c: rng.random_sample(n) for c in range(2, steps + 1)}
+    pf = S.ParticleFilter(n, spec["og"], spec["sm"])
+    assert pf.geom.G == 2001 and pf.geom.numSpokes == 720 and pf.engine.volume_shape(0) == (70, 13, 13)
+    _warm(S, pf, scene)
+    for count, fr in enumerate(scene["frames"][:steps], start=1):
+        pf._update(0, n, fr, count, uniforms=uniforms.get(count))
+    rawW = pf.weights.cpu().numpy().copy()
+    pf.weightUnbalanced()
+    ref = _oracle_slots(spec, scene, range(n), uniforms, steps)
+    poses = pf.poses()
+    for i in range(n):
+        p = ref[i]
+        assert poses[i].tolist() == [p.prevMatchedReading[k] for k in ("x", "y", "theta")], i
+        assert rawW[i] == pytest.approx(p.weight, rel=1e-9, abs=0)
+        assert np.array_equal(pf.particles[i].og.occupancyGridTotal, p.og.occupancyGridTotal)
+        assert np.array_equal(pf.particles[i].og.occupancyGridVisited, p.og.occupancyGridVisited)
+
+
+def test_c5_workload_full_circle_2001_lattice_matches_oracle(S):
+    """The bench's c5 workload (360 beams over 2*pi, 2001^2 lattice, 0.05 m cells), sampling mode, 2 particles."""
+    from slam_2d_lidar_scan_b200 import synthetic
+    spec = synthetic.config("c5")
+    scene = synthetic.make_scene(seed=0, steps=4, K=360, fov=2 * np.pi, unit=0.05)
+    n, steps = 2, 3
+    rng = np.random.RandomState(6)
+    uniforms = {c: rng.random_sample(n) for c in range(2, steps + 1)}
+    pf = S.ParticleFilter(n, spec["og"], spec["sm"])
+    _warm(S, pf, scene)
+    for count, fr in enumerate(scene["frames"][:steps], start=1):
+        pf._update(0, n, fr, count, uniforms=uniforms.get(count))
+    pf.weightUnbalanced()
+    ref = _oracle_slots(spec, scene, range(n), uniforms, steps)
+    for i in range(n):
+        p = ref[i]
+        assert pf.poses()[i].tolist() == [p.prevMatchedReading[k] for k in ("x", "y", "theta")], i
+        assert np.array_equal(pf.particles[i].og.occupancyGridTotal, p.og.occupancyGridTotal)
+
+
+def test_global_slot_plan_in_sampling_mode_matches_oracle(S, frames):
+    """Reference default geometry (0.02 m cells, 1241^2 fine field -> the SLOW global-slot plan) with matchMax=False:
+    both sides draw from numpy's global RandomState, so they run one after the other from the same seed."""
+    init = {"x": frames[0]["x"], "y": frames[0]["y"]}
+
+    def run(mod, steps=8):
+        np.random.seed(13)
+        og = mod.OccupancyGrid(*OG_02(init))
+        sm = mod.ScanMatcher(og, *SM_02)
+        poses, confs = [], []
+        xT, yT = [], []
+        for count, fr in enumerate(frames[:steps], start=1):
+            cur = reading(fr)
+            if count == 1:
+                prevRawTh = prevMatchedTh = None
+                matched, conf = cur, 1
+            else:
+                ex, ey, eth, dist, estTh, rawTh = O.propose_pose(cur, prevMatched, prevRaw, prevRawTh, prevMatchedTh)
+                matched, conf = sm.matchScan({'x': ex, 'y': ey, 'theta': eth, 'range': cur['range']}, dist, estTh, count,
+                                             matchMax=False)
+                prevRawTh = rawTh
+                prevMatchedTh = O.moving_heading(matched['x'], matched['y'], xT[-1], yT[-1])
+            og.updateOccupancyGrid(matched)
+            xT.append(matched['x']); yT.append(matched['y'])
+            prevMatched, prevRaw = matched, cur
+            poses.append([matched['x'], matched['y'], matched['theta']])
+            confs.append(conf)
+        return og, np.array(poses), np.array(confs, dtype=np.float64), np.random.random_sample()
+    og, poses, confs, nxt = run(S)
+    plan = (S._native.C.c_int * 8)()
+    S._native.lib.slam_matcher_plan(S.ScanMatcher(og, *SM_02).engine.handle, 1, S._native.C.byref(plan))
+    assert plan[2] == 0                                   # bitmaps in the global slot: this IS the SLOW plan
+    rog, rposes, rconfs, rnxt = run(O)
+    assert np.array_equal(poses, rposes) and nxt == rnxt
+    np.testing.assert_allclose(confs, rconfs, rtol=CONF_RTOL, atol=0)
+    assert np.array_equal(og.occupancyGridTotal, rog.occupancyGridTotal)
+    assert len(np.unique(poses[:, 2] - np.array([f["theta"] for f in frames[:8]]))) > 1
+
+
+def test_fastslam_step_facade_matches_oracle_loop(S, frames):
+    """FastSLAM.step(reading) == the loop body of Algorithm/FastSlam.py:159-162 (update, trigger, resample)."""
+    init = {"x": frames[0]["x"], "y": frames[0]["y"]}
+    ogp, smp = [30, 30, init, 0.1, np.pi, 10, 180, 0.5], [1.0, 0.3, 2, 0.1, 0.25, 0.3, 0.15, 2]
+    np.random.seed(8)
+    fs = S.FastSLAM(5, ogp, smp)
+    fired = [fs.step(reading(fr)) for fr in frames[:10]]
+    got = fs.pf.poses()
+    nxt = np.random.random_sample()
+    np.random.seed(8)
+    ref = O.ParticleFilter(5, ogp, smp)
+    want = []
+    for count, fr in enumerate(frames[:10], start=1):
+        ref.updateParticles(reading(fr), count)
+        f = ref.weightUnbalanced()
+        if f:
+            ref.resample()
+        want.append(f)
+    assert fired == want and fs.count == 10 and fs.resampled == want
+    assert np.array_equal(got, _poses(ref)) and nxt == np.random.random_sample()
+    np.testing.assert_allclose(fs.pf.weights.cpu().numpy(), [p.weight for p in ref.particles], rtol=1e-9, atol=0)
+    for i in (0, 4):
+        assert np.array_equal(fs.pf.particles[i].og.occupancyGridTotal, ref.particles[i].og.occupancyGridTotal)
+
+
+@pytest.mark.parametrize("tag,og,sm", [("c3", lambda i: (72, 72, i, 0.05, np.pi, 180, 10, 0.25), SM_C3),
+                                       ("ref02", lambda i: (72, 72, i, 0.02, np.pi, 180, 10, 5 * 0.02), SM_02)])
+def test_whole_intel_log_matches_reference_golden(S, tag, og, sm):
+    """All 910 readings of intel_gfs through the deterministic driver on a pre-sized 72 m map: every pose, confidence and
+    the final count sums equal the unmodified reference's (tests/golden/make_golden.py --full)."""
+    full, g = load_golden("intel_full.npz"), load_golden("det_intel_full.npz")
+    fr = [dict(x=float(p[0]), y=float(p[1]), theta=float(p[2]), range=r.tolist()) for p, r in zip(full["poses"], full["ranges"])]
+    init = {"x": fr[0]["x"], "y": fr[0]["y"]}
+    grid, poses, confs, _ = drive(S, fr, og(init), sm, len(fr))
+    assert np.array_equal(poses, g[tag + "_poses"])
+    assert np.array_equal(sha(poses), g[tag + "_sha"])
+    np.testing.assert_allclose(confs, g[tag + "_confs"], rtol=CONF_RTOL, atol=0)
+    dg = grid.device_grid[:, :grid.geom.G].to(torch.float64)
+    mask = (dg[..., 0] != 1) | (dg[..., 1] != 2)          # the golden sums run over the touched cells
+    got = [float(dg[..., 0][mask].sum().item()), float(dg[..., 1][mask].sum().item()), float(mask.sum().item())]
+    assert got == g[tag + "_sums"].tolist()
+
+
+def test_translation_by_whole_cells_shifts_the_result(S, frames):
+    """SURVEY section 4 property: moving the map origin and every pose by k*unit moves the matched pose by k*unit and
+    leaves the argmax indices and the map counts unchanged (the binary fraction 2^-4 keeps the shift exact)."""
+    outs = []
+    for shift in (0.0, 64 * 0.0625):
+        init = {"x": 1.0 + shift, "y": -2.0 + shift}
+        og = S.OccupancyGrid(40, 40, init, 0.0625, np.pi, 180, 10, 0.25)
+        sm = S.ScanMatcher(og, 1.5, 0.3, 2, 0.1, 0.25, 0.3, 0.15, 5)
+        idxs, poses = [], []
+        for count, fr in enumerate(frames[:6], start=1):
+            rd = reading(fr)
+            rd["x"], rd["y"] = init["x"] + 0.0625 * round((fr["x"] - frames[0]["x"]) / 0.0625), \
+                init["y"] + 0.0625 * round((fr["y"] - frames[0]["y"]) / 0.0625)
+            m, c = sm.matchScan(rd, 0.1, None, count)
+            if count > 1:
+                idxs.append(sm.lastIdx)
+            og.updateOccupancyGrid(m)
+            poses.append([m["x"] - shift, m["y"] - shift, m["theta"]])
+        outs.append((idxs, np.array(poses), og.occupancyGridTotal.copy()))
+    assert outs[0][0] == outs[1][0]
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])

@@ -1,47 +1,92 @@
-"""Aggregate an ncu source-page CSV of match.cu by kernel phase (line ranges): samples, instructions, top stalls.
-python tools/ncu_by_phase.py file.csv"""
+"""Aggregate an ncu source-page CSV (`ncu -i rep --page source --csv --print-source cuda,sass`) of match.cu by kernel
+phase: warp-instructions executed, stall samples and the top stall reasons per phase.
+
+SASS instructions inlined from other files (common.cuh's dadd/ddiv, CUDA intrinsics headers) are attributed to the
+phase of the nearest preceding match.cu line in ADDRESS order, so the table follows the machine code layout.
+Phase boundaries are found from marker strings in the captured source itself (no hard-coded line numbers).
+
+    python tools/ncu_by_phase.py file.csv [particles] [source.csv from --print-source cuda of the same report]
+"""
 import csv
 import sys
 from collections import defaultdict
 
-RANGES = [  # (first line, last line, phase) in csrc/match.cu -- keep in sync when the file moves
-    (174, 335, "scores: gathers + pairwise sums"), (342, 431, "lists: sort/unique"), (440, 463, "block reductions"),
-    (480, 737, "blur (D1 dilate + D2)"), (750, 803, "scores: task loop/epilogue"), (811, 831, "lists: batch loop"),
-    (832, 846, "union window geometry"), (854, 990, "stream warps (TMA + pack)"), (1004, 1065, "A/B geometry, clear, maps"),
-    (1066, 1267, "C scatter + transpose"), (1268, 1308, "D/E blur call, min/clamp"), (1309, 1349, "F points"),
-    (1350, 1384, "G lists+scores driver"), (1385, 1506, "H select"), (1507, 1561, "kernel main loop"),
-    (114, 173, "helpers (lds, mbarrier wait, tma)"), (44, 61, "csync"),
+MARKS = [  # (marker text in match.cu, phase name) -- a phase runs from its marker to the next one
+    ("struct FetchDense", "scores: gather + pairwise"), ("__noinline__ double block_sum", "select: leaf sums"),
+    ("void warp_sort", "lists: sort"), ("void build_list", "lists: rotate/unique"), ("struct BlockScratch", "block reductions"),
+    ("__noinline__ void blur_stage", "blur D1 dilate + tiles"), ("// D2. active tiles", "blur D2"),
+    ("struct ScoreArgs", "scores: task loop/epilogue"), ("__noinline__ void lists_batch", "lists: batch loop"),
+    ("void union_window", "union window geometry"), ("void pack_rows", "stream: pack"), ("__noinline__ void stream_role", "stream: TMA/role"),
+    ("__device__ void run_stage", "A geometry"), ("// ---- B. clear", "B clear + maps"), ("// ---- C. occupied", "C scatter setup"),
+    ("    if (mode == 1) {", "C scatter shift"), ("    } else if (mode == 2) {", "C scatter range"), ("    } else {\n", "C scatter generic"),
+    ("    if (mode != 0) {      // transposed", "C transpose"), ("// ---- D. separable", "D/E call, min/clamp"),
+    ("// ---- F. beam", "F points"), ("// ---- G. per-theta", "G driver"), ("// ---- H. select", "H select"),
+    ("__global__ void __launch_bounds__", "kernel main loop"), ("__global__ void lut_kernel", "other kernels"),
 ]
+
 rows = list(csv.reader(open(sys.argv[1])))
+nPart = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 cur = hdr = None
-agg = defaultdict(lambda: [0, 0, defaultdict(int)])
+line = None
+addr = {}          # address -> dict(file, line, samples, inst, stalls)
+src = {}           # match.cu line -> text
 for r in rows:
     if len(r) >= 2 and r[0] == "File Path":
-        cur = r[1]; continue
+        cur = r[1].split('/')[-1]
+        continue
     if len(r) > 2 and r[0] == "Line No":
-        hdr = r; continue
-    if hdr and len(r) >= 10 and r[0].isdigit():
-        d = dict(zip(hdr, r))
+        hdr = r
+        continue
+    if not hdr or len(r) < 10:
+        continue
+    if r[0].isdigit():
+        line = int(r[0])
+        if cur == "match.cu":
+            src[line] = r[1]
+        continue
+    if r[2].startswith("0x"):
+        d = dict(zip(hdr[4:], r[4:]))
         try:
             smp, inst = int(d["# Samples"]), int(d["Instructions Executed"])
         except (KeyError, ValueError):
             continue
-        fn = cur.split('/')[-1]
-        ln = int(r[0])
-        key = fn
-        if fn == "match.cu":
-            key = "match.cu:other"
-            for a, b, name in RANGES:
-                if a <= ln <= b:
-                    key = name; break
-        e = agg[key]
-        e[0] += smp; e[1] += inst
-        for k, v in d.items():
-            if k.startswith("stall_") and "Not Issued" not in k and v.isdigit():
-                e[2][k[6:]] += int(v)
-ts = sum(e[0] for e in agg.values()) or 1
-ti = sum(e[1] for e in agg.values()) or 1
-print("total samples %d, warp-instructions %d" % (ts, ti))
-for k, e in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-    top = sorted(e[2].items(), key=lambda kv: -kv[1])[:4]
-    print("%5.1f%% smp %5.1f%% inst  %-36s %s" % (100 * e[0] / ts, 100 * e[1] / ti, k, " ".join("%s=%d" % t for t in top)))
+        st = {k[6:]: int(v) for k, v in d.items() if k.startswith("stall_") and "Not Issued" not in k and v.isdigit() and int(v)}
+        addr[int(r[2], 16)] = dict(file=cur, line=line, smp=smp, inst=inst, st=st, sass=r[3].strip())
+
+if len(sys.argv) > 3:      # full source text as captured in the report (lines without SASS are absent from `src`)
+    for r in csv.reader(open(sys.argv[3])):
+        if len(r) >= 2 and r[0].isdigit():
+            src[int(r[0])] = r[1]
+bounds = []
+for text, name in MARKS:
+    hit = [ln for ln, s in src.items() if text.strip("\n") in s and (not text.endswith("\n") or s.rstrip() == text.rstrip("\n"))]
+    if hit:
+        bounds.append((min(hit), name))
+bounds.sort()
+
+
+def phase_of(ln):
+    name = "helpers / prologue"
+    for b, n in bounds:
+        if ln >= b:
+            name = n
+    return name
+
+
+agg = defaultdict(lambda: [0, 0, defaultdict(int)])
+last = "helpers / prologue"
+for a in sorted(addr):
+    e = addr[a]
+    if e["file"] == "match.cu":
+        last = phase_of(e["line"])
+    g = agg[last]
+    g[0] += e["smp"]; g[1] += e["inst"]
+    for k, v in e["st"].items():
+        g[2][k] += v
+ts = sum(g[0] for g in agg.values()) or 1
+ti = sum(g[1] for g in agg.values()) or 1
+print("total samples %d, warp-instructions %d (%.0f per particle)" % (ts, ti, ti / nPart))
+for k, g in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+    top = sorted(g[2].items(), key=lambda kv: -kv[1])[:5]
+    print("%5.1f%% smp %5.1f%% inst %8.0f inst/particle  %-28s %s" % (100 * g[0] / ts, 100 * g[1] / ti, g[1] / nPart, k,
+                                                                   " ".join("%s=%d" % t for t in top)))

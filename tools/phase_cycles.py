@@ -52,9 +52,9 @@ for st in range(2):
     for k in range(7 if st == 0 else 6):
         v = per[8 * st + k]
         print("%-7s %-12s %10.0f cycles/particle  %5.1f %%" % ("coarse" if st == 0 else "fine", names[k], v, 100 * v / tot))
-sub = ["B clear+maps", "C scatter", "C transpose", "-", "D1 dilate", "D2 blur (own tiles)"]
+sub = ["B clear+maps", "C scatter", "C transpose", "-", "D1 dilate", "D2 blur (own tiles)", "-", "-", "H argmax", "H exp", "H sum", "H cdf"]
 for st in range(2):
-    print("  sub-phases %s: " % ("coarse" if st == 0 else "fine") + ", ".join("%s %.0f" % (sub[k], per[16 + 16 * st + k]) for k in range(6) if sub[k] != "-"))
+    print("  sub-phases %s: " % ("coarse" if st == 0 else "fine") + ", ".join("%s %.0f" % (sub[k], per[16 + 16 * st + k]) for k in range(12) if sub[k] != "-"))
 per[16:] = 0
 print("stream warp: TMA wait %.0f, pack %.0f, bitmap-free wait %.0f cycles/particle" % (per[7], per[14], per[15]))
 per[7] = per[14] = per[15] = 0
