@@ -33,11 +33,14 @@ namespace slam {
 constexpr int NSW = SLAM_STREAM_WARPS;   // stream warps: TMA producers / occupancy-bit packers of the union window.  The
                                  // shared-memory pipe serves warps round-robin, so a stream warp reads its ring at 1/16
                                  // of the pipe (measured): NSW sets the stream rate (2.5 MB per particle at c3)
-constexpr int NT = 512 - 32 * NSW;   // compute threads per CTA: 16 warps x 128 registers in all (4 per scheduler)
+#ifndef SLAM_CTA_THREADS
+#define SLAM_CTA_THREADS 512
+#endif
+constexpr int NT_ALL = SLAM_CTA_THREADS;   // 512 threads x 128 registers (4 warps per scheduler)
+constexpr int NT = NT_ALL - 32 * NSW;   // compute threads per CTA
 constexpr int NW = NT / 32;      // compute warps per CTA
 constexpr int NWC = NW;          // compute warps
 constexpr int NTC = NWC * 32;    // compute threads
-constexpr int NT_ALL = 512;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int RING_STAGES = NSW > 2 ? 2 * NSW : 4;   // TMA ring depth over all stream warps (stages of ringRows window rows each)
 constexpr int RING_PER_WARP = RING_STAGES / NSW;
@@ -332,44 +335,6 @@ __device__ __forceinline__ bool pairwise_g(const F& f, int n, double (&out)[GRP]
   }
   return false;
 }
-
-// numpy pairwise_sum, n <= 128 branch (8 running lanes, fixed tree, sequential tail)
-template <class F>
-__device__ __noinline__ double block_sum(const F f, int off, int n) {
-  if (n < 8) {
-    double res = 0.0;
-    for (int i = 0; i < n; ++i) res = dadd(res, f(off + i));
-    return res;
-  }
-  double r0 = f(off), r1 = f(off + 1), r2 = f(off + 2), r3 = f(off + 3);
-  double r4 = f(off + 4), r5 = f(off + 5), r6 = f(off + 6), r7 = f(off + 7);
-  int m = n - (n & 7);
-  for (int i = 8; i < m; i += 8) {
-    double a0 = f(off + i), a1 = f(off + i + 1), a2 = f(off + i + 2), a3 = f(off + i + 3);
-    double a4 = f(off + i + 4), a5 = f(off + i + 5), a6 = f(off + i + 6), a7 = f(off + i + 7);
-    r0 = dadd(r0, a0); r1 = dadd(r1, a1); r2 = dadd(r2, a2); r3 = dadd(r3, a3);
-    r4 = dadd(r4, a4); r5 = dadd(r5, a5); r6 = dadd(r6, a6); r7 = dadd(r7, a7);
-  }
-  double res = dadd(dadd(dadd(r0, r1), dadd(r2, r3)), dadd(dadd(r4, r5), dadd(r6, r7)));
-  for (int i = m; i < n; ++i) res = dadd(res, f(off + i));
-  return res;
-}
-
-// numpy pairwise_sum recursion (n > 128: split at n/2 rounded down to a multiple of 8); depth 3 covers n <= 512
-template <int D, class F>
-__device__ __forceinline__ double pairwise(const F& f, int off, int n) {
-  if (D == 0 || n <= 128) return block_sum(f, off, n);
-  int n2 = n / 2;
-  n2 -= n2 % 8;
-  double a = pairwise<(D > 0 ? D - 1 : 0)>(f, off, n2);
-  double b = pairwise<(D > 0 ? D - 1 : 0)>(f, off + n2, n - n2);
-  return dadd(a, b);
-}
-
-struct SmemVal {
-  const double* a;
-  __device__ __forceinline__ double operator()(int k) const { return a[k]; }
-};
 
 // bitonic sort of 32*E keys held E per lane (element index = lane*E + e), ascending
 template <int E>
@@ -936,6 +901,13 @@ __device__ __forceinline__ void union_window(const MatchParams& P, int p, int (&
   w[0] = y0; w[1] = x0; w[2] = min(max(y1 - y0, 0), P.URows); w[3] = nc;
 }
 
+// Cold start: nothing overlaps the stream of a CTA's FIRST particle, so the compute warps pack most of its rows
+// themselves with plain loads (rows >= first_rows_by_stream) while the stream warps take the head of the window.
+__device__ __forceinline__ int first_rows_by_stream(int rows, int rowsPerChunk) {
+  const int q = rowsPerChunk * NSW;
+  return min(rows, max(q, (rows / 4) / q * q));
+}
+
 // mbarriers of the stream pipeline (static shared memory)
 struct StreamShared {
   unsigned long long ringFull[RING_STAGES];   // TMA complete_tx: a ring stage has landed
@@ -1016,7 +988,7 @@ __device__ __noinline__ void stream_role(const MatchParams& P, const CUtensorMap
       const int pP = (int)blockIdx.x + kP * (int)gridDim.x;
       if (nChP < 0) {
         union_window(P, pP, wP);
-        nChP = my_chunks(wP[2]);
+        nChP = my_chunks(kP == 0 ? first_rows_by_stream(wP[2], BY) : wP[2]);
         cP = 0;
       }
       if (cP >= nChP) { ++kP; nChP = -1; continue; }
@@ -1034,7 +1006,8 @@ __device__ __noinline__ void stream_role(const MatchParams& P, const CUtensorMap
     const int p = (int)blockIdx.x + k * (int)gridDim.x, b = k & 1;
     int w[4];
     union_window(P, p, w);
-    const int nCh = my_chunks(w[2]);
+    const int rowsMine = k == 0 ? first_rows_by_stream(w[2], BY) : w[2];     // rows this pipeline covers
+    const int nCh = my_chunks(rowsMine);
     unsigned* U = Ubuf0 + (size_t)b * P.URows * UW;
     top_up();                                                     // loads of this (and the next) particle in flight
     if (cyc) cyc[15] -= clock64();
@@ -1049,8 +1022,8 @@ __device__ __noinline__ void stream_role(const MatchParams& P, const CUtensorMap
       const unsigned stage = ring + st * stageBytes;
       for (int r = 0; r < BY; r += 2) {            // two rows per batch (a stage row pitch inside a box is BX cells)
         const int row = (sw + c * NSW) * BY + r;
-        if (row >= w[2]) break;
-        const int nr = min(min(2, BY - r), w[2] - row);
+        if (row >= rowsMine) break;
+        const int nr = min(min(2, BY - r), rowsMine - row);
         const unsigned rowS = stage + (unsigned)(r * BX * 8);
         unsigned* Urow = U + (size_t)row * UW;
         switch (nTW) {      // 64-cell groups per row: compile-time trip counts for the common window sizes
@@ -1514,11 +1487,20 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
     csync();
     sc.mark(9);    // H exp
     double* leafSum = sbuf<double>(S.oLeaf);
-    SmemVal sv;
-    sv.a = scores;
-    for (int l = tid; l < S.nLeaves; l += NTC) {
-      int2 lf = S.leaves[l];
-      leafSum[l] = block_sum(sv, lf.x, lf.y);
+    // leaves of numpy's pairwise sum: eight threads per leaf, thread l owns the running lane r[l]
+    for (int g0 = warp * 4; g0 < S.nLeaves; g0 += NWC * 4) {
+      const int g = g0 + (lane >> 3), l = lane & 7;
+      const bool valid = g < S.nLeaves;
+      const int2 lf = valid ? S.leaves[g] : make_int2(0, 0);
+      const int off = lf.x, n = lf.y, m = n - (n & 7);
+      double r = (n >= 8) ? scores[off + l] : 0.0;
+      for (int i = 8; i < m; i += 8) r = dadd(r, scores[off + i + l]);
+      r = dadd(r, __shfl_xor_sync(FULL, r, 1));        // (r0+r1), (r2+r3), ...
+      r = dadd(r, __shfl_xor_sync(FULL, r, 2));        // ((r0+r1)+(r2+r3)), ...
+      r = dadd(r, __shfl_xor_sync(FULL, r, 4));
+      if (n < 8) r = 0.0;
+      for (int i = (n < 8 ? 0 : m); i < n; ++i) r = dadd(r, scores[off + i]);     // n < 8: plain sequential sum; else the tail
+      if (valid && l == 0) leafSum[g] = r;
     }
     csync();
     if (warp == 0) {   // combine the leaves along numpy's recursion tree, one tree level at a time
@@ -1637,6 +1619,44 @@ __global__ void __launch_bounds__(NT_ALL, 1) match_kernel(const __grid_constant_
   Ubuf[0] = reinterpret_cast<unsigned*>(gslot + P.gU);
   Ubuf[1] = Ubuf[0] + (size_t)P.URows * P.UW;
   long long* cyc = P.dbgCycles ? P.dbgCycles + (size_t)blockIdx.x * 48 : nullptr;   // [0..15] phases, [16..47] sub-phases
+  if ((int)blockIdx.x < P.N) {      // cold start: the tail rows of the first particle's union window, 2 rows per warp at a time
+    const int p = blockIdx.x, lane = ctid() & 31, warp = ctid() >> 5;
+    if (cyc && ctid() == 0) { const long long t = clock64(); cyc[6] -= t; cyc[29] -= t; }     // accounted as waiting for the union bitmap
+    int w[4];
+    union_window(P, p, w);
+    const int r0 = first_rows_by_stream(w[2], P.ringRows);
+    const int nTW = P.UWcells / 64, UW = P.UW, nc = w[3];
+    const float2* base = reinterpret_cast<const float2*>(P.grid) + ((size_t)p * P.G + w[0]) * P.pitch + w[1];
+    for (int row = r0 + warp; row < w[2]; row += NWC) {
+      const float2* src = base + (size_t)row * P.pitch;
+      unsigned* Urow = Ubuf[0] + (size_t)row * UW;
+      for (int t0 = 0; t0 < nTW; t0 += 10) {         // 10 16-byte loads (a whole row at c3) in flight per lane
+        float4 v[10];                                // lane L of group t: cells 64t + 2L, 64t + 2L + 1
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+          const int c = 64 * (t0 + j) + 2 * lane;    // nc is even: both cells are inside the window or neither is
+          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (t0 + j < nTW && c < nc) v[j] = ld_stream_f4(reinterpret_cast<const float4*>(src + c));
+        }
+        unsigned wd[20];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {               // visited/total > 0.5 (:29-31); bit i of a plain word = cell i
+          const unsigned pq = (2.f * v[j].x > v[j].y ? 1u : 0u) | (2.f * v[j].z > v[j].w ? 2u : 0u);
+          const unsigned lo = __shfl_sync(FULL, pq, lane >> 1), hi = __shfl_sync(FULL, pq, 16 + (lane >> 1));
+          wd[2 * j] = __ballot_sync(FULL, (lo >> (lane & 1)) & 1u);
+          wd[2 * j + 1] = __ballot_sync(FULL, (hi >> (lane & 1)) & 1u);
+        }
+        if (lane == 0) {                               // out-of-window cells were loaded as zeros -> zero bits
+#pragma unroll
+          for (int j = 0; j < 20; j += 4)
+            if (2 * t0 + j < UW) *reinterpret_cast<uint4*>(Urow + 2 * t0 + j) = make_uint4(wd[j], wd[j + 1], wd[j + 2], wd[j + 3]);
+        }
+      }
+      if (lane == 0)
+        for (int t = 20 * ((nTW + 9) / 10); t < UW; t += 4) *reinterpret_cast<uint4*>(Urow + t) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (cyc && ctid() == 0) { const long long t = clock64(); cyc[6] += t; cyc[29] += t; }
+  }
   int k = 0;
   for (int p = blockIdx.x; p < P.N; p += gridDim.x, ++k) {
     const double x = P.estPose[3 * p], y = P.estPose[3 * p + 1], th = P.estPose[3 * p + 2];
@@ -1648,9 +1668,12 @@ __global__ void __launch_bounds__(NT_ALL, 1) match_kernel(const __grid_constant_
     const unsigned* Ucur = Ubuf[k & 1];
     const int* wcur = s_uwin[k & 1];
     const unsigned uEmpty = smem_u32(&ss.uEmpty[k & 1]);
-    if (cyc && ctid() == 0) cyc[6] -= clock64();
-    mbar_wait(smem_u32(&ss.uFull[k & 1]), (unsigned)((k >> 1) & 1));   // this particle's union bitmap is complete
-    if (cyc && ctid() == 0) cyc[6] += clock64();
+    if (cyc && ctid() == 0) { const long long t = clock64(); cyc[6] -= t; if (k == 0) cyc[28] -= t; }
+    // this particle's union bitmap is complete: one thread polls the mbarrier, the others park at the named barrier
+    // (14 spinning warps would take issue slots from the stream warps they are waiting for)
+    if (ctid() == 0) mbar_wait(smem_u32(&ss.uFull[k & 1]), (unsigned)((k >> 1) & 1));
+    csync();
+    if (cyc && ctid() == 0) { const long long t = clock64(); cyc[6] += t; if (k == 0) cyc[28] += t; }
     if (P.fast) {      // everything but the sparse fine field lives in shared memory
       run_stage<true, true>(P, P.st[0], 0, p, x, y, th, sample, u, gslot, bs, status, c, cyc, Ucur, wcur, 0u);
       run_stage<true, false>(P, P.st[1], 1, p, c.x, c.y, c.th, false, 0.0, gslot, bs, status, f, cyc2, Ucur, wcur, uEmpty);
@@ -1866,8 +1889,8 @@ static int plan_stage(slam_matcher* m, const slam_geometry* g, const slam_stage_
     S.oDil = S.bitsInSmem ? take(bitsBytes) : 0;      // activity bitmap lives through the correlation
     S.oDx = take(dxyBytes);
     S.oDy = take(dxyBytes);
-    S.oVw = take((size_t)NW * VW_PER_WARP * 8);
     const size_t common = off;
+    S.oVw = take((size_t)NW * VW_PER_WARP * 8);       // first-pass values of the blur: aliased by the correlate-phase buffers
     // window / blur-phase buffers
     S.oBits = S.bitsInSmem ? take(bitsBytes) : 0;
     S.oBitsT = S.bitsInSmem ? take(bitsTBytes) : 0;

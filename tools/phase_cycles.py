@@ -55,6 +55,7 @@ for st in range(2):
 sub = ["B clear+maps", "C scatter", "C transpose", "-", "D1 dilate", "D2 blur (own tiles)", "-", "-", "H argmax", "H exp", "H sum", "H cdf"]
 for st in range(2):
     print("  sub-phases %s: " % ("coarse" if st == 0 else "fine") + ", ".join("%s %.0f" % (sub[k], per[16 + 16 * st + k]) for k in range(12) if sub[k] != "-"))
+print("cold start per CTA: compute-side pack %.0f, then wait for the stream warps %.0f cycles" % (c[:, 29].sum() / (2 * ctas), c[:, 28].sum() / (2 * ctas)))
 per[16:] = 0
 print("stream warp: TMA wait %.0f, pack %.0f, bitmap-free wait %.0f cycles/particle" % (per[7], per[14], per[15]))
 per[7] = per[14] = per[15] = 0
