@@ -79,6 +79,7 @@ struct StageDev {
   int levelStart[24];
   // ---- plan
   int Wmax, Wmap, words, WT, Ppitch, TB, Kpad, E;   // words includes >= 1 always-zero spare word per row
+  int nGrpPad;               // score tasks per offset row (>= ceil(nOff / GRP); padded so that dense gathers are bank-conflict free)
   int bitsInSmem, PInSmem, scoresInSmem, needScores;
   int oBits, oBitsT, oDil, oVw, oRow, oCol, oTiles, oP, oLists, oCnt, oScores, oDx, oDy, oLeaf;
   int tileCap;                 // capacity of one warp's private segment of the active-tile list
@@ -122,6 +123,11 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)_
 __device__ __forceinline__ unsigned lds_u32(unsigned a) {
   unsigned v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u32x4(unsigned a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
   return v;
 }
 __device__ __forceinline__ double lds_f64(unsigned a) {
@@ -184,12 +190,18 @@ struct FetchDense {
   unsigned baseS;        // shared address of the field
   unsigned off;          // (dx << 16) + dy, added to the key in one go
   int pitch;
-  __device__ __forceinline__ void get(int k, double (&v)[GRP]) const {
-    const unsigned sxy = lds_u32(listS + 4u * k) + off;
+  // keys of points k .. k+7 (k a multiple of 8: two 16-byte broadcast loads instead of eight 4-byte ones)
+  __device__ __forceinline__ void keys8(int k, unsigned (&key)[8]) const {
+    const uint4 a = lds_u32x4(listS + 4u * k), b = lds_u32x4(listS + 4u * k + 16u);
+    key[0] = a.x; key[1] = a.y; key[2] = a.z; key[3] = a.w; key[4] = b.x; key[5] = b.y; key[6] = b.z; key[7] = b.w;
+  }
+  __device__ __forceinline__ void get_key(unsigned key, double (&v)[GRP]) const {
+    const unsigned sxy = key + off;
     const unsigned a = baseS + 8u * ((sxy & 0xffffu) * pitch + (sxy >> 16));
 #pragma unroll
     for (int g = 0; g < GRP; ++g) v[g] = lds_f64(a + 8u * g);
   }
+  __device__ __forceinline__ void get(int k, double (&v)[GRP]) const { get_key(lds_u32(listS + 4u * k), v); }
 };
 
 // Sparse field: materialised (already clamped) only where the activity bitmap is set; everywhere else it equals the
@@ -204,13 +216,21 @@ struct FetchGated {
   double B2;
   unsigned off;          // (dx << 16) + dy
   int pitch, words;
-  __device__ __forceinline__ void get(int k, double (&v)[GRP]) const {
-    unsigned sxy, w0, w1;
+  __device__ __forceinline__ void keys8(int k, unsigned (&key)[8]) const {
+    uint4 a, b;
     if (FAST) {
-      sxy = lds_u32(listS + 4u * k) + off;
+      a = lds_u32x4(listS + 4u * k); b = lds_u32x4(listS + 4u * k + 16u);
     } else {
-      sxy = list[k] + off;
+      a = *reinterpret_cast<const uint4*>(list + k); b = *reinterpret_cast<const uint4*>(list + k + 4);
     }
+    key[0] = a.x; key[1] = a.y; key[2] = a.z; key[3] = a.w; key[4] = b.x; key[5] = b.y; key[6] = b.z; key[7] = b.w;
+  }
+  __device__ __forceinline__ void get(int k, double (&v)[GRP]) const {
+    get_key(FAST ? lds_u32(listS + 4u * k) : list[k], v);
+  }
+  __device__ __forceinline__ void get_key(unsigned key, double (&v)[GRP]) const {
+    unsigned w0, w1;
+    const unsigned sxy = key + off;
     const unsigned xx = sxy >> 16, yy = sxy & 0xffffu;
     const unsigned wi = yy * words + (xx >> 5);
     if (FAST) {
@@ -432,6 +452,9 @@ struct BlockScratch {
   int ival[NWC];
   double bcast[4];
   double incumbent;                // branch-and-bound: best finished score of the fine stage so far
+  double wbest[NWC];               // per-warp first maximum of the score volume so far (merged batch by batch) ...
+  int wbestIdx[NWC];               // ... and its flat index; -1 = none yet
+  int nanFlag;                     // a NaN score was seen
   int ibcast[8];
   unsigned maskA[64], maskB[64];   // per union-bitmap word: window columns whose index-map offset is D / D-1
 };
@@ -633,24 +656,38 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
     for (int base = 0; base < nList; base += TG) {
       int ti[TG], tw[TG];
       unsigned dls[TG];
+      bool interior = true;      // no tile of the group touches a reflected border (identical in every lane)
 #pragma unroll
       for (int u = 0; u < TG; ++u) {
-        const int tt = base + u < nList ? (int)myTiles[base + u] : -1;
-        dls[u] = tt >= 0 ? dil[tt] : 0u;
-        ti[u] = tt < 0 ? 0 : (int)__umulhi((unsigned)tt, wordsMagic);      // tt / words (tt < 2^16: exact)
-        tw[u] = tt < 0 ? 0 : tt - ti[u] * words;
+        const bool real = base + u < nList;
+        const int tt = (int)myTiles[real ? base + u : base];               // padding repeats the group's first tile ...
+        dls[u] = real ? dil[tt] : 0u;                                      // ... with no active cell
+        ti[u] = (int)__umulhi((unsigned)tt, wordsMagic);      // tt / words (tt < 2^16: exact)
+        tw[u] = tt - ti[u] * words;
+        interior = interior && ti[u] >= R && ti[u] + R < Wy && 32 * tw[u] >= R && 32 * tw[u] + 31 + R < Wx;
       }
       // virtual columns 32w-r .. 32w+31+r of every tile: lane handles vc0 = 32w-r+lane and (lane < 2r) vc1 = vc0+32
       unsigned sr[TG][2];
+      if (__all_sync(FULL, interior)) {
+        // the column's 2r+1 rows straight out of the transposed bitmap; columns and rows need no reflection
 #pragma unroll
-      for (int u = 0; u < TG; ++u) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int i = ti[u];
-          const int col = reflect_idx(32 * tw[u] - R + lane + 32 * h, Wx);
+        for (int u = 0; u < TG; ++u) {
+          const int lo = ti[u] - R;
+          const unsigned* colBits = bitsT + (32 * tw[u] - R + lane) * WT + (lo >> 5);
+          const unsigned* colBits1 = colBits + (lane < 2 * R ? 32 * WT : 0);     // lanes >= 2r: value unused
+          sr[u][0] = __funnelshift_r(colBits[0], colBits[1], lo & 31) & patMask;
+          sr[u][1] = __funnelshift_r(colBits1[0], colBits1[1], lo & 31) & patMask;
+        }
+      } else {
+#pragma unroll 1
+        for (int uh = 0; uh < 2 * TG; ++uh) {
+          const int u = uh >> 1, h = uh & 1;
+          const int i = u == 0 ? ti[0] : (u == 1 ? ti[1] : (u == 2 ? ti[2] : ti[3]));
+          const int twu = u == 0 ? tw[0] : (u == 1 ? tw[1] : (u == 2 ? tw[2] : tw[3]));
+          const int col = reflect_idx(32 * twu - R + lane + 32 * h, Wx);
           const unsigned* colBits = bitsT + col * WT;
           unsigned pat;
-          if (i - R >= 0 && i + R < Wy) {       // the column's 2r+1 rows straight out of the transposed bitmap
+          if (i - R >= 0 && i + R < Wy) {
             const int lo = i - R;
             pat = __funnelshift_r(colBits[lo >> 5], colBits[(lo >> 5) + 1], lo & 31) & patMask;
           } else {                              // top / bottom border: reflected rows, bit by bit
@@ -660,7 +697,10 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
               pat |= ((colBits[rr >> 5] >> (rr & 31)) & 1u) << (d + R);
             }
           }
-          sr[u][h] = pat;
+#pragma unroll
+          for (int u2b = 0; u2b < TG; ++u2b) {
+            if (u2b == u) { if (h == 0) sr[u2b][0] = pat; else sr[u2b][1] = pat; }
+          }
         }
       }
       double vv[TG][2];
@@ -700,7 +740,7 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           if ((act4 >> e) & 1u) {
-            mn = fmin(mn, val[e]);
+            if (!anyInactive) mn = fmin(mn, val[e]);    // otherwise probMin == B2 is already known
             out[e] = val[e] > thr ? 0.0 : val[e];       // clamp (:44)
           }
         }
@@ -782,15 +822,17 @@ struct ScoreArgs {
   double B2, thr;
   size_t gP, gDil, gScores;
   int oLists, oCnt, oP, oDil, oScores, needScores;
-  int Kpad, Pp, words, nHalf, nOff, nt, t0;
+  int Kpad, Pp, words, nHalf, nOff, nt, t0, nGrpPad;
   unsigned bestS;       // shared address of the branch-and-bound incumbent (fine stage)
   double* bestP;        // the same as a pointer
+  BlockScratch* bs;     // per-warp running maxima / NaN flag (results leave through shared memory: by-reference
+                        // results would be promoted to registers that are reserved along the whole call chain)
 };
 
 // Score volume of a batch of thetas (phase G2).  Kept out of line so the hot gather loop gets its own register
 // allocation instead of inheriting the pressure of the rest of the fused kernel.
 template <bool FAST, bool DENSE, bool PRUNE>
-__device__ __noinline__ void score_batch(const ScoreArgs& A, double& bestIO, int& bestIdxIO, int& nanIO) {
+__device__ __noinline__ void score_batch(const ScoreArgs& A) {
   const unsigned* lists = sbuf<unsigned>(A.oLists);
   const int* cnts = sbuf<int>(A.oCnt);
   const double* Pf = DENSE ? sbuf<double>(A.oP) : reinterpret_cast<const double*>(A.gslot + A.gP);
@@ -798,11 +840,11 @@ __device__ __noinline__ void score_batch(const ScoreArgs& A, double& bestIO, int
   double* scores = A.needScores ? buf<FAST, double>(A.oScores, A.gslot, A.gScores) : nullptr;
   const int tid = ctid();
   const int nOff = A.nOff, nOff2 = nOff * nOff;
-  const int nGrp = (nOff + GRP - 1) / GRP;
+  const int nGrp = A.nGrpPad;        // tasks per offset row; tasks with b0 >= nOff are padding (idle lanes)
   const int perTheta = nOff * nGrp;
   const int nq = A.nt * perTheta;
-  double best = bestIO;
-  int bestIdx = bestIdxIO, sawNan = nanIO;
+  double best = 0.0;
+  int bestIdx = -1, sawNan = 0;
   PruneCtx pc;
   pc.bestS = A.bestS; pc.h1 = 0; pc.validMask = 0;
 #pragma unroll
@@ -815,6 +857,7 @@ __device__ __noinline__ void score_batch(const ScoreArgs& A, double& bestIO, int
       tl = (tl & 1) ? mid - 1 - (tl >> 1) : mid + (tl >> 1);
     }
     const int a = rem0 / nGrp, b0 = (rem0 - a * nGrp) * GRP;
+    if (b0 >= nOff) continue;
     double sc[GRP];
     bool pruned = false;
     if (DENSE) {
@@ -856,7 +899,21 @@ __device__ __noinline__ void score_batch(const ScoreArgs& A, double& bestIO, int
       }
     }
   }
-  bestIO = best; bestIdxIO = bestIdx; nanIO = sawNan;
+  // first maximum in C order over the warp, merged into the warp's running maximum of the earlier batches
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const double ob = __shfl_xor_sync(FULL, best, d);
+    const int oi = __shfl_xor_sync(FULL, bestIdx, d);
+    if (oi >= 0 && (bestIdx < 0 || ob > best || (ob == best && oi < bestIdx))) { best = ob; bestIdx = oi; }
+  }
+  sawNan = __any_sync(FULL, sawNan);
+  if ((tid & 31) == 0) {
+    const int warp = tid >> 5;
+    const double ob = A.bs->wbest[warp];
+    const int oi = A.bs->wbestIdx[warp];
+    if (bestIdx >= 0 && (oi < 0 || best > ob || (best == ob && bestIdx < oi))) { A.bs->wbest[warp] = best; A.bs->wbestIdx[warp] = bestIdx; }
+    if (sawNan) A.bs->nanFlag = 1;
+  }
 }
 
 struct ListArgs {
@@ -1057,24 +1114,54 @@ __device__ __noinline__ void stream_role(const MatchParams& P, const CUtensorMap
   }
 }
 
+// What the phases of one stage hand to each other (shared memory).  Every phase is an out-of-line function called
+// from a thin driver: under the call ABI a callee only gets the registers its caller does not keep live across the
+// call, and with the whole stage in one function the gather / blur loops were scheduled with a single load in flight.
+struct StageCtx {
+  double cx, cy, cth;      // centre of the search (proposal, or the coarse result)
+  double xr0, yr0;         // window origin (:21-22)
+  double thr;              // clamp threshold 0.5 * probMin (:44)
+  int Wx, Wy, K0;          // field size, beams < maxRange
+};
+
 struct StageOut {
   double x, y, th, conf;
   int it, ia, ib;
 };
 
+// All static shared memory of the CTA behind one pointer: the per-particle driver keeps (almost) nothing live across
+// the phase calls, so every phase gets the whole register file.
+struct CtaShared {
+  StreamShared ss;
+  BlockScratch bs;
+  StageCtx ctx;
+  StageOut res[2];         // coarse / fine result of the current particle
+  int uwin[2][4];          // union window (row0, col0, rows, cols) of the two bitmaps in flight
+};
+
+// ---- phases A-C: window geometry, index maps, occupied cells of the window
 template <bool FAST, bool DENSE>
-__device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, int p, double cx, double cy, double cth,
-                          bool sample, double uniform, unsigned char* gslot, BlockScratch& bs, int& status,
-                          StageOut& out, long long* cyc, const unsigned* U, const int* uwin, unsigned uEmptyBar) {
+__device__ __noinline__ void window_phase(const MatchParams& P, CtaShared& sh, int stageId, int k, int& status) {
+  const StageDev& S = P.st[stageId];
+  StageCtx& ctx = sh.ctx;
+  BlockScratch& bs = sh.bs;
+  long long* cyc = P.dbgCycles ? P.dbgCycles + (size_t)blockIdx.x * 48 + 8 * stageId : nullptr;   // [0..15] phases of the two stages
+  unsigned char* gslot = P.scratch + (size_t)blockIdx.x * P.slotBytes;
   const int tid = ctid(), lane = tid & 31, warp = tid >> 5;
   const double ul = S.unitLength;
-  const int r = S.r;
-
+  const int words = S.words, Pp = S.Ppitch;
+  long long* sub = cyc ? cyc + (stageId == 0 ? 16 : 24) : nullptr;     // sub-phase slots (cyc is already offset by 8 for stage 1)
+  (void)gslot; (void)lane; (void)warp; (void)ul; (void)words; (void)Pp; (void)sub;
+  const double cx = ctx.cx, cy = ctx.cy;
+  const unsigned* U = reinterpret_cast<const unsigned*>(gslot + P.gU) + (size_t)(k & 1) * P.URows * P.UW;   // this particle's union bitmap
+  const int* uwin = sh.uwin[k & 1];
+  const unsigned uEmptyBar = stageId == 1 ? smem_u32(&sh.ss.uEmpty[k & 1]) : 0u;     // the fine stage is its last reader
   // ---- A. geometry of the search window (ScanMatcher_OGBased.py:21-28)
   const double xr0 = dsub(cx, P.R), xr1 = dadd(cx, P.R);
   const double yr0 = dsub(cy, P.R), yr1 = dadd(cy, P.R);
   const int Wx = (int)ddiv(dsub(xr1, xr0), ul) + 1;
   const int Wy = (int)ddiv(dsub(yr1, yr0), ul) + 1;
+  if (tid == 0) { ctx.xr0 = xr0; ctx.yr0 = yr0; ctx.Wx = Wx; ctx.Wy = Wy; }     // published by the barriers below
   int mx0 = (int)rint(ddiv(dsub(xr0, P.mapX0), P.unit)), mx1 = (int)rint(ddiv(dsub(xr1, P.mapX0), P.unit));
   int my0 = (int)rint(ddiv(dsub(yr0, P.mapY0), P.unit)), my1 = (int)rint(ddiv(dsub(yr1, P.mapY0), P.unit));
   if (xr0 < P.mapX0 || xr1 > P.mapX1 || yr0 < P.mapY0 || yr1 > P.mapY1) status |= SLAM_ST_WINDOW_OUTSIDE_MAP;
@@ -1082,7 +1169,6 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
   mx1 = min(mx1, P.G); my1 = min(my1, P.G);
   mx1 = min(mx1, mx0 + S.Wmap); my1 = min(my1, my0 + S.Wmap);
   const int ncols = max(mx1 - mx0, 0), nrows = max(my1 - my0, 0);
-  const int words = S.words;
 
   unsigned* bits = buf<FAST, unsigned>(S.oBits, gslot, S.gBits);
   unsigned* bitsT = buf<FAST, unsigned>(S.oBitsT, gslot, S.gBitsT);    // [col][WT] transposed
@@ -1091,12 +1177,10 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
   short* rowMap = sbuf<short>(S.oRow);
   short* colMap = sbuf<short>(S.oCol);
   double* Pf = DENSE ? sbuf<double>(S.oP) : reinterpret_cast<double*>(gslot + S.gP);
-  const int Pp = S.Ppitch;
   constexpr bool dense = DENSE;                      // coarse: dense field in shared memory, ungated gathers
 
   csync();  // previous users of the arena are done
   if (cyc && tid == 0) cyc[0] -= clock64();
-  long long* sub = cyc ? cyc + (stageId == 0 ? 16 : 32) - (stageId == 0 ? 0 : 8) : nullptr;   // cyc is already offset by 8 for stage 1
   SubCyc sc;
   sc.start(sub);
 
@@ -1333,7 +1417,26 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
   sc.mark(2);      // C transposes (or the whole generic scatter)
   if (uEmptyBar && tid == 0) mbar_arrive(uEmptyBar);   // last reader of the union bitmap: the stream warp may reuse it
   if (cyc && tid == 0) { long long t = clock64(); cyc[0] += t; cyc[1] -= t; }
+}
 
+// ---- phases D-F: blur, min / clamp, beam end points
+template <bool FAST, bool DENSE>
+__device__ __noinline__ void field_phase(const MatchParams& P, CtaShared& sh, int stageId, int p, int& status) {
+  const StageDev& S = P.st[stageId];
+  StageCtx& ctx = sh.ctx;
+  BlockScratch& bs = sh.bs;
+  long long* cyc = P.dbgCycles ? P.dbgCycles + (size_t)blockIdx.x * 48 + 8 * stageId : nullptr;   // [0..15] phases of the two stages
+  unsigned char* gslot = P.scratch + (size_t)blockIdx.x * P.slotBytes;
+  const int tid = ctid(), lane = tid & 31, warp = tid >> 5;
+  const double ul = S.unitLength;
+  const int words = S.words, Pp = S.Ppitch;
+  long long* sub = cyc ? cyc + (stageId == 0 ? 16 : 24) : nullptr;     // sub-phase slots (cyc is already offset by 8 for stage 1)
+  (void)gslot; (void)lane; (void)warp; (void)ul; (void)words; (void)Pp; (void)sub;
+  const double cx = ctx.cx, cy = ctx.cy, cth = ctx.cth;
+  const int Wx = ctx.Wx, Wy = ctx.Wy, r = S.r;
+  unsigned* dil = buf<FAST, unsigned>(S.oDil, gslot, S.gDil);         // activity bitmap
+  double* Pf = DENSE ? sbuf<double>(S.oP) : reinterpret_cast<double*>(gslot + S.gP);
+  constexpr bool dense = DENSE;
   // ---- D. separable blur in scipy's order, only where the result can differ from the background.
   double mn = 0.0;                 // every field value is <= 0
   int nActive = 0;
@@ -1413,24 +1516,41 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
     }
     K0 = base;
   }
+  if (tid == 0) { ctx.K0 = K0; ctx.thr = thr; }
   csync();
 
-  if (cyc && tid == 0) cyc[2] += clock64();
+  if (cyc && tid == 0) cyc[2] += clock64();}
+
+// ---- phase G: per-theta point lists and the score volume
+template <bool FAST, bool DENSE>
+__device__ __noinline__ void correlate_phase(const MatchParams& P, CtaShared& sh, int stageId, int p, int& status) {
+  const StageDev& S = P.st[stageId];
+  StageCtx& ctx = sh.ctx;
+  BlockScratch& bs = sh.bs;
+  long long* cyc = P.dbgCycles ? P.dbgCycles + (size_t)blockIdx.x * 48 + 8 * stageId : nullptr;   // [0..15] phases of the two stages
+  unsigned char* gslot = P.scratch + (size_t)blockIdx.x * P.slotBytes;
+  const int tid = ctid(), lane = tid & 31, warp = tid >> 5;
+  const double ul = S.unitLength;
+  const int words = S.words, Pp = S.Ppitch;
+  long long* sub = cyc ? cyc + (stageId == 0 ? 16 : 24) : nullptr;     // sub-phase slots (cyc is already offset by 8 for stage 1)
+  (void)gslot; (void)lane; (void)warp; (void)ul; (void)words; (void)Pp; (void)sub;
+  const double cx = ctx.cx, cy = ctx.cy, xr0 = ctx.xr0, yr0 = ctx.yr0, thr = ctx.thr;
+  const int Wx = ctx.Wx, Wy = ctx.Wy, K0 = ctx.K0;
   // ---- G. per-theta lists + score volume, TB thetas at a time
   double* scores = S.needScores ? buf<FAST, double>(S.oScores, gslot, S.gScores) : nullptr;
   double* dvol = P.dbgVol[stageId] ? P.dbgVol[stageId] + (size_t)p * S.nPoses : nullptr;
   const int nOff = S.nOff, nOff2 = nOff * nOff;
   const double* rv = (stageId == 0) ? P.rv : nullptr;
   const double* tw = (stageId == 0 && P.tw) ? P.tw + (size_t)p * nOff2 : nullptr;
-  double best = 0.0;
-  int bestIdx = -1;
-  int sawNan = 0;
+  if (lane == 0) { bs.wbest[warp] = 0.0; bs.wbestIdx[warp] = -1; }      // own slot: ordered by program order within the warp
+  if (tid == 0) bs.nanFlag = 0;                                          // read after the barriers below
   ScoreArgs SA;
+  SA.bs = &bs;
   SA.gslot = gslot; SA.rv = rv; SA.tw = tw; SA.dvol = dvol; SA.B2 = S.B2; SA.thr = thr;
   SA.gP = S.gP; SA.gDil = S.gDil; SA.gScores = S.gScores;
   SA.oLists = S.oLists; SA.oCnt = S.oCnt; SA.oP = S.oP; SA.oDil = S.oDil; SA.oScores = S.oScores;
   SA.needScores = S.needScores;
-  SA.Kpad = S.Kpad; SA.Pp = Pp; SA.words = words; SA.nHalf = S.nHalf; SA.nOff = nOff;
+  SA.Kpad = S.Kpad; SA.Pp = Pp; SA.words = words; SA.nHalf = S.nHalf; SA.nOff = nOff; SA.nGrpPad = S.nGrpPad;
   // exact branch-and-bound only where nothing but the argmax is needed (fine stage, no volume dump)
   const bool prune = !DENSE && stageId == 1 && !S.needScores && !dvol && !rv && !tw && !P.noPrune;
   SA.bestP = &bs.incumbent; SA.bestS = smem_u32(&bs.incumbent);
@@ -1449,31 +1569,44 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
     csync();
     if (cyc && tid == 0) { long long t = clock64(); cyc[3] += t; cyc[4] -= t; }
     SA.nt = nt; SA.t0 = t0;
-    if (prune) score_batch<FAST, DENSE, true>(SA, best, bestIdx, sawNan);
-    else score_batch<FAST, DENSE, false>(SA, best, bestIdx, sawNan);
+    if (prune) score_batch<FAST, DENSE, true>(SA);
+    else score_batch<FAST, DENSE, false>(SA);
     csync();
     if (cyc && tid == 0) cyc[4] += clock64();
   }
-  if (cyc && tid == 0) cyc[5] -= clock64();
-  sc.start(sub);
+}
 
+// ---- phase H: argmax / softmax-CDF sample, confidence, matched pose
+template <bool FAST, bool DENSE>
+__device__ __noinline__ void select_phase(const MatchParams& P, CtaShared& sh, int stageId, int p, int& status) {
+  const StageDev& S = P.st[stageId];
+  StageCtx& ctx = sh.ctx;
+  BlockScratch& bs = sh.bs;
+  long long* cyc = P.dbgCycles ? P.dbgCycles + (size_t)blockIdx.x * 48 + 8 * stageId : nullptr;   // [0..15] phases of the two stages
+  unsigned char* gslot = P.scratch + (size_t)blockIdx.x * P.slotBytes;
+  const int tid = ctid(), lane = tid & 31, warp = tid >> 5;
+  const double ul = S.unitLength;
+  const int words = S.words, Pp = S.Ppitch;
+  long long* sub = cyc ? cyc + (stageId == 0 ? 16 : 24) : nullptr;     // sub-phase slots (cyc is already offset by 8 for stage 1)
+  (void)gslot; (void)lane; (void)warp; (void)ul; (void)words; (void)Pp; (void)sub;
+  const double cx = ctx.cx, cy = ctx.cy, cth = ctx.cth;
+  const int nOff = S.nOff, nOff2 = nOff * nOff;
+  double* scores = S.needScores ? buf<FAST, double>(S.oScores, gslot, S.gScores) : nullptr;
+  const bool sample = stageId == 0 && P.uniforms != nullptr;      // the fine stage always takes the argmax (:73)
+  const double uniform = sample ? P.uniforms[p] : 0.0;
+  StageOut out;
+  if (cyc && tid == 0) cyc[5] -= clock64();
+  SubCyc sc;
+  sc.start(sub);
   // ---- H. select (:133-141)
-  if (csync_or(sawNan)) status |= SLAM_ST_NAN_SCORE;
+  if (bs.nanFlag) status |= SLAM_ST_NAN_SCORE;      // (the correlate phase ended with a barrier)
   int chosen;
-  {  // first maximum in C order
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      double ob = __shfl_xor_sync(FULL, best, d);
-      int oi = __shfl_xor_sync(FULL, bestIdx, d);
-      if (oi >= 0 && (bestIdx < 0 || ob > best || (ob == best && oi < bestIdx))) { best = ob; bestIdx = oi; }
-    }
-    if (lane == 0) { bs.dval[warp] = best; bs.ival[warp] = bestIdx; }
-    csync();
-    double b = bs.dval[0];
-    int bi = bs.ival[0];
+  {  // first maximum in C order: the per-warp maxima of the correlate phase
+    double b = bs.wbest[0];
+    int bi = bs.wbestIdx[0];
     for (int w2 = 1; w2 < NWC; ++w2) {
-      double ob = bs.dval[w2];
-      int oi = bs.ival[w2];
+      double ob = bs.wbest[w2];
+      int oi = bs.wbestIdx[w2];
       if (oi >= 0 && (bi < 0 || ob > b || (ob == b && oi < bi))) { b = ob; bi = oi; }
     }
     chosen = bi;
@@ -1595,31 +1728,32 @@ __device__ void run_stage(const MatchParams& P, const StageDev& S, int stageId, 
   out.y = dadd(cy, dmul((double)(ia - S.nHalf), ul));
   out.th = dadd(cth, S.thetas[it]);
   out.conf = conf;
+  if (tid == 0) sh.res[stageId] = out;      // read after the next barrier
   if (cyc && tid == 0) cyc[5] += clock64();
 }
 
-__global__ void __launch_bounds__(NT_ALL, 1) match_kernel(const __grid_constant__ MatchParams P,
-                                                           const __grid_constant__ CUtensorMap tmap) {
-  __shared__ BlockScratch bs;
-  __shared__ int s_uwin[2][4];
-  __shared__ __align__(8) StreamShared ss;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < RING_STAGES; ++i) mbar_init(smem_u32(&ss.ringFull[i]), 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&ss.uFull[i]), 32 * NSW); mbar_init(smem_u32(&ss.uEmpty[i]), 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+template <bool FAST, bool DENSE>
+__device__ __forceinline__ void run_stage(const MatchParams& P, CtaShared& sh, int stageId, int p, int k, int& status) {
+  csync();                // the previous stage's readers of ctx are done, its result is published
+  if (ctid() == 0) {
+    StageCtx& ctx = sh.ctx;
+    if (stageId == 0) { ctx.cx = P.estPose[3 * p]; ctx.cy = P.estPose[3 * p + 1]; ctx.cth = P.estPose[3 * p + 2]; }
+    else { ctx.cx = sh.res[0].x; ctx.cy = sh.res[0].y; ctx.cth = sh.res[0].th; }     // centred on the coarse result (:66-73)
   }
-  __syncthreads();
-  // warp NWC: union-window stream (TMA producer + bit packer), runs up to one particle ahead of the compute warps
-  if (threadIdx.x < 32 * NSW) {
-    stream_role(P, &tmap, ss, s_uwin);
-    return;
-  }
+  csync();
+  window_phase<FAST, DENSE>(P, sh, stageId, k, status);
+  field_phase<FAST, DENSE>(P, sh, stageId, p, status);
+  correlate_phase<FAST, DENSE>(P, sh, stageId, p, status);
+  select_phase<FAST, DENSE>(P, sh, stageId, p, status);
+}
+
+// Cold start: nothing overlaps the stream of a CTA's FIRST particle, so the compute warps pack the tail rows of its
+// union window themselves, 2 rows per warp at a time.
+__device__ __noinline__ void cold_start(const MatchParams& P) {
   unsigned char* gslot = P.scratch + (size_t)blockIdx.x * P.slotBytes;
-  unsigned* Ubuf[2];
-  Ubuf[0] = reinterpret_cast<unsigned*>(gslot + P.gU);
-  Ubuf[1] = Ubuf[0] + (size_t)P.URows * P.UW;
-  long long* cyc = P.dbgCycles ? P.dbgCycles + (size_t)blockIdx.x * 48 : nullptr;   // [0..15] phases, [16..47] sub-phases
-  if ((int)blockIdx.x < P.N) {      // cold start: the tail rows of the first particle's union window, 2 rows per warp at a time
+  unsigned* Ubuf0 = reinterpret_cast<unsigned*>(gslot + P.gU);
+  long long* cyc = P.dbgCycles ? P.dbgCycles + (size_t)blockIdx.x * 48 : nullptr;
+  {
     const int p = blockIdx.x, lane = ctid() & 31, warp = ctid() >> 5;
     if (cyc && ctid() == 0) { const long long t = clock64(); cyc[6] -= t; cyc[29] -= t; }     // accounted as waiting for the union bitmap
     int w[4];
@@ -1629,7 +1763,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) match_kernel(const __grid_constant_
     const float2* base = reinterpret_cast<const float2*>(P.grid) + ((size_t)p * P.G + w[0]) * P.pitch + w[1];
     for (int row = r0 + warp; row < w[2]; row += NWC) {
       const float2* src = base + (size_t)row * P.pitch;
-      unsigned* Urow = Ubuf[0] + (size_t)row * UW;
+      unsigned* Urow = Ubuf0 + (size_t)row * UW;
       for (int t0 = 0; t0 < nTW; t0 += 10) {         // 10 16-byte loads (a whole row at c3) in flight per lane
         float4 v[10];                                // lane L of group t: cells 64t + 2L, 64t + 2L + 1
 #pragma unroll
@@ -1657,39 +1791,53 @@ __global__ void __launch_bounds__(NT_ALL, 1) match_kernel(const __grid_constant_
     }
     if (cyc && ctid() == 0) { const long long t = clock64(); cyc[6] += t; cyc[29] += t; }
   }
-  int k = 0;
-  for (int p = blockIdx.x; p < P.N; p += gridDim.x, ++k) {
-    const double x = P.estPose[3 * p], y = P.estPose[3 * p + 1], th = P.estPose[3 * p + 2];
-    int status = 0;
-    StageOut c, f;
-    const bool sample = P.uniforms != nullptr;
-    const double u = sample ? P.uniforms[p] : 0.0;
-    long long* cyc2 = cyc ? cyc + 8 : nullptr;
-    const unsigned* Ucur = Ubuf[k & 1];
-    const int* wcur = s_uwin[k & 1];
-    const unsigned uEmpty = smem_u32(&ss.uEmpty[k & 1]);
-    if (cyc && ctid() == 0) { const long long t = clock64(); cyc[6] -= t; if (k == 0) cyc[28] -= t; }
-    // this particle's union bitmap is complete: one thread polls the mbarrier, the others park at the named barrier
-    // (14 spinning warps would take issue slots from the stream warps they are waiting for)
-    if (ctid() == 0) mbar_wait(smem_u32(&ss.uFull[k & 1]), (unsigned)((k >> 1) & 1));
-    csync();
-    if (cyc && ctid() == 0) { const long long t = clock64(); cyc[6] += t; if (k == 0) cyc[28] += t; }
-    if (P.fast) {      // everything but the sparse fine field lives in shared memory
-      run_stage<true, true>(P, P.st[0], 0, p, x, y, th, sample, u, gslot, bs, status, c, cyc, Ucur, wcur, 0u);
-      run_stage<true, false>(P, P.st[1], 1, p, c.x, c.y, c.th, false, 0.0, gslot, bs, status, f, cyc2, Ucur, wcur, uEmpty);
-    } else {           // large windows: bitmaps / fields / scores in the global slot
-      run_stage<false, false>(P, P.st[0], 0, p, x, y, th, sample, u, gslot, bs, status, c, cyc, Ucur, wcur, 0u);
-      run_stage<false, false>(P, P.st[1], 1, p, c.x, c.y, c.th, false, 0.0, gslot, bs, status, f, cyc2, Ucur, wcur, uEmpty);
-    }
-    status = block_or(status, bs);
-    if (ctid() == 0) {
-      P.outPose[3 * p] = f.x; P.outPose[3 * p + 1] = f.y; P.outPose[3 * p + 2] = f.th;
-      P.outConf[p] = c.conf;
-      int* o = P.outIdx + 6 * p;
-      o[0] = c.it; o[1] = c.ia; o[2] = c.ib; o[3] = f.it; o[4] = f.ia; o[5] = f.ib;
-      P.status[p] |= status;     // OR: bits raised earlier in the step (slam_propose_poses) survive
-    }
+}
+
+// One particle: wait for its union bitmap, coarse stage, fine stage, results.
+__device__ __noinline__ void match_particle(const MatchParams& P, CtaShared& sh, int p, int k) {
+  long long* cyc = P.dbgCycles ? P.dbgCycles + (size_t)blockIdx.x * 48 : nullptr;   // [0..15] phases, [16..47] sub-phases
+  int status = 0;
+  if (cyc && ctid() == 0) { const long long t = clock64(); cyc[6] -= t; if (k == 0) cyc[28] -= t; }
+  // this particle's union bitmap is complete: one thread polls the mbarrier, the others park at the named barrier
+  // (14 spinning warps would take issue slots from the stream warps they are waiting for)
+  if (ctid() == 0) mbar_wait(smem_u32(&sh.ss.uFull[k & 1]), (unsigned)((k >> 1) & 1));
+  csync();
+  if (cyc && ctid() == 0) { const long long t = clock64(); cyc[6] += t; if (k == 0) cyc[28] += t; }
+  if (P.fast) {      // everything but the sparse fine field lives in shared memory
+    run_stage<true, true>(P, sh, 0, p, k, status);
+    run_stage<true, false>(P, sh, 1, p, k, status);
+  } else {           // large windows: bitmaps / fields / scores in the global slot
+    run_stage<false, false>(P, sh, 0, p, k, status);
+    run_stage<false, false>(P, sh, 1, p, k, status);
   }
+  status = block_or(status, sh.bs);
+  if (ctid() == 0) {
+    const StageOut c = sh.res[0], f = sh.res[1];
+    P.outPose[3 * p] = f.x; P.outPose[3 * p + 1] = f.y; P.outPose[3 * p + 2] = f.th;
+    P.outConf[p] = c.conf;
+    int* o = P.outIdx + 6 * p;
+    o[0] = c.it; o[1] = c.ia; o[2] = c.ib; o[3] = f.it; o[4] = f.ia; o[5] = f.ib;
+    P.status[p] |= status;     // OR: bits raised earlier in the step (slam_propose_poses) survive
+  }
+}
+
+__global__ void __launch_bounds__(NT_ALL, 1) match_kernel(const __grid_constant__ MatchParams P,
+                                                           const __grid_constant__ CUtensorMap tmap) {
+  __shared__ __align__(16) CtaShared sh;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RING_STAGES; ++i) mbar_init(smem_u32(&sh.ss.ringFull[i]), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&sh.ss.uFull[i]), 32 * NSW); mbar_init(smem_u32(&sh.ss.uEmpty[i]), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // warps 0 .. NSW-1: union-window stream (TMA producer + bit packer), runs up to one particle ahead of the compute warps
+  if (threadIdx.x < 32 * NSW) {
+    stream_role(P, &tmap, sh.ss, sh.uwin);
+    return;
+  }
+  if ((int)blockIdx.x < P.N) cold_start(P);
+  int k = 0;
+  for (int p = blockIdx.x; p < P.N; p += gridDim.x, ++k) match_particle(P, sh, p, k);
 }
 
 // First-pass (axis 0) value for every occupancy pattern of a column's 2r+1 rows; same operation order as scipy:
@@ -1868,12 +2016,43 @@ static int plan_stage(slam_matcher* m, const slam_geometry* g, const slam_stage_
   const size_t scoreBytes = S.needScores ? (size_t)S.nPoses * 8 : 0;
   const size_t leafBytes = S.needScores ? (size_t)(S.nLeaves + S.nOps) * 8 : 0;
   const size_t dxyBytes = align_up((size_t)g->K * 8, 16);
-  // field pitch: conflict-free shared-memory gathers want pitch == nOff (mod 16) doubles
+  // Field pitch and score-task layout.  A warp's 32 score tasks (same theta, same point k) read GRP adjacent doubles
+  // of consecutive offset rows.  For the dense shared-memory field the (pitch, tasks per row) pair is chosen by
+  // simulating the bank conflicts of those 64-bit loads (16 double-wide banks, one wavefront per distinct address
+  // and bank within a half-warp): padding a row of 7 tasks to 8 lets two rows interleave on even / odd banks.
   int pp = S.Wmax;
-  if (stageId == 0)
+  S.nGrpPad = (S.nOff + GRP - 1) / GRP;
+  if (stageId == 0 && fast) {
+    double bestCost = 1e300;
+    const int nGrp0 = (S.nOff + GRP - 1) / GRP;
+    for (int pad = nGrp0; pad <= ((nGrp0 + 7) & ~7); ++pad) {
+      for (int cand = S.Wmax; cand < S.Wmax + 16; ++cand) {
+        const int per = S.nOff * pad;
+        long long waves = 0;
+        for (int q0 = 0; q0 < per; q0 += 16) {          // half-warps of one theta (theta boundaries ignored)
+          int cnt[16][16], nb[16];
+          for (int b = 0; b < 16; ++b) nb[b] = 0;
+          int mx = 0;
+          for (int l = 0; l < 16 && q0 + l < per; ++l) {
+            const int q = q0 + l, a = q / pad, b0 = (q - a * pad) * GRP;
+            if (b0 >= S.nOff) continue;
+            const int addr = a * cand + b0, bank = addr & 15;
+            bool dup = false;
+            for (int j = 0; j < nb[bank]; ++j) dup |= cnt[bank][j] == addr;
+            if (!dup) cnt[bank][nb[bank]++] = addr;
+            mx = std::max(mx, nb[bank]);
+          }
+          waves += mx;
+        }
+        const double cost = (double)waves + 1e-3 * (cand - S.Wmax);      // ties: the smaller pitch
+        if (cost < bestCost) { bestCost = cost; pp = cand; S.nGrpPad = pad; }
+      }
+    }
+  } else if (stageId == 0) {
     while ((pp % 16) != (S.nOff % 16)) ++pp;
-  else
+  } else {
     pp = (pp + 3) & ~3;
+  }
   S.Ppitch = pp;
   const size_t PBytes = (size_t)(S.Wmax + 1) * S.Ppitch * 8;   // one slack row: grouped gathers may overshoot
   // FAST plan: bitmaps, lists, scores (and the dense coarse field) in shared memory; SLOW plan: global slot.

@@ -6,5 +6,5 @@ cd "$(dirname "$0")/.."
 name=$1; shift
 mkdir -p build
 cd slam-2d-lidar-scan_b200/csrc
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false -std=c++17 -Xcompiler -fPIC -shared "$@" \
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false -std=c++17 -rdc=true -maxrregcount=128 -Xcompiler -fPIC -shared "$@" \
   -o ../../build/libslam2d_$name.so api.cu match.cu update.cu filter.cu

@@ -12,16 +12,16 @@ import sys
 from collections import defaultdict
 
 MARKS = [  # (marker text in match.cu, phase name) -- a phase runs from its marker to the next one
-    ("struct FetchDense", "scores: gather + pairwise"), ("__noinline__ double block_sum", "select: leaf sums"),
+    ("struct FetchDense", "scores: fetch dense"), ("struct FetchGated", "scores: fetch gated"), ("struct PruneCtx", "scores: pairwise"),
     ("void warp_sort", "lists: sort"), ("void build_list", "lists: rotate/unique"), ("struct BlockScratch", "block reductions"),
     ("__noinline__ void blur_stage", "blur D1 dilate + tiles"), ("// D2. active tiles", "blur D2"),
     ("struct ScoreArgs", "scores: task loop/epilogue"), ("__noinline__ void lists_batch", "lists: batch loop"),
-    ("void union_window", "union window geometry"), ("void pack_rows", "stream: pack"), ("__noinline__ void stream_role", "stream: TMA/role"),
+    ("void union_window", "union window geometry"), ("float2 lds_f2", "stream: pack"), ("__noinline__ void stream_role", "stream: TMA/role"),
     ("__device__ void run_stage", "A geometry"), ("// ---- B. clear", "B clear + maps"), ("// ---- C. occupied", "C scatter setup"),
     ("    if (mode == 1) {", "C scatter shift"), ("    } else if (mode == 2) {", "C scatter range"), ("    } else {\n", "C scatter generic"),
     ("    if (mode != 0) {      // transposed", "C transpose"), ("// ---- D. separable", "D/E call, min/clamp"),
     ("// ---- F. beam", "F points"), ("// ---- G. per-theta", "G driver"), ("// ---- H. select", "H select"),
-    ("__global__ void __launch_bounds__", "kernel main loop"), ("__global__ void lut_kernel", "other kernels"),
+    ("__global__ void __launch_bounds__", "kernel main loop + cold start"), ("__global__ void lut_kernel", "other kernels"),
 ]
 
 rows = list(csv.reader(open(sys.argv[1])))
@@ -53,7 +53,10 @@ for r in rows:
         st = {k[6:]: int(v) for k, v in d.items() if k.startswith("stall_") and "Not Issued" not in k and v.isdigit() and int(v)}
         addr[int(r[2], 16)] = dict(file=cur, line=line, smp=smp, inst=inst, st=st, sass=r[3].strip())
 
-if len(sys.argv) > 3:      # full source text as captured in the report (lines without SASS are absent from `src`)
+if len(sys.argv) > 3 and sys.argv[3].endswith(".cu"):      # the source file itself (must be the captured version)
+    for i, l in enumerate(open(sys.argv[3]).read().split("\n"), start=1):
+        src[i] = l
+elif len(sys.argv) > 3:      # full source text as captured in the report (lines without SASS are absent from `src`)
     for r in csv.reader(open(sys.argv[3])):
         if len(r) >= 2 and r[0].isdigit():
             src[int(r[0])] = r[1]
