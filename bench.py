@@ -10,7 +10,13 @@ holds the workload's particle count (c3: 1024 particles, 1001x1001 lattices @0.0
   value   whole-job particle-scans/s with the step's inputs already resident in HBM (pre-staged), CUDA-event timed
   e2e     the same through the public API (ParticleFilter.updateParticles + weightUnbalanced) with HOST readings:
           per step one pinned H2D copy (ranges | uniforms | radial prior) and a D2H read of (variance, trigger, status)
-  roofline  fused match kernel: N * B_match algorithmic bytes / its mean CUDA-event duration, vs the measured HBM peak
+  roofline  fused match kernel: N * B_match algorithmic bytes / its mean CUDA-event duration, vs the measured HBM peak;
+          `traffic` comes from profiles/r2_match_traffic.json only while that file's hash of csrc/match.cu + common.cuh
+          still matches the sources (tools/ncu_traffic.py stamps it), else null
+  timing  the K-step schedule is replayed until the timed region is >= ~1 s (`repeats`, `timed_steps`; a replay
+          restarts from the same particle poses, the lattices keep integrating), so that the clock sampler sees tens
+          of loaded samples; the synthetic odometry steps 0.35 m, so the reference's heading
+          prior (mode 1, priors_kernel) is part of every timed step; `kernel_ms` = mean CUDA-event duration per launch
   cpu_baseline  the oracle port of the reference's numpy path on the host cores (rank 0, N=1, bounded sample)
 
 --impl reference times the oracle port (the reference is pure Python and is not present on the GPU box) on all
@@ -33,6 +39,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "particle-scans/s (180-beam scan matched + mapped per particle)"
+STRIDE = 0.35          # synthetic odometry step [m]: > 0.3 m, so the heading prior is active (FastSlam.py:88)
+MIN_TIMED_S = 1.0      # the timed regions run at least this long
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
@@ -42,7 +50,7 @@ def _cpu_worker(args):
     from oracle import slam_oracle as O
     spec = importlib_pkg().synthetic.config(workload)
     scene = importlib_pkg().synthetic.make_scene(seed=0, steps=steps + 1, K=spec["K"], fov=spec["og"][4],
-                                                 unit=spec["og"][3])
+                                                 unit=spec["og"][3], stride=STRIDE)
     np.random.seed(seed)
     p = O.Particle(spec["og"], spec["sm"])
     for fr in scene["warm"]:
@@ -146,14 +154,24 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def kernel_source_hash():
+    """sha256 over the sources of the match kernel: a traffic capture is only valid for the code it was taken from."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("match.cu", "common.cuh"):
+        h.update(open(os.path.join(ROOT, "slam-2d-lidar-scan_b200", "csrc", f), "rb").read())
+    return h.hexdigest()
+
+
 def measured_traffic(workload, nLocal):
     """dram__bytes_read.sum + dram__bytes_write.sum of one match_kernel launch from the committed `ncu --set full`
-    capture of this same command (profiles/r1_match_traffic.json), or None if no capture matches the workload."""
+    capture (profiles/r2_match_traffic.json, written by tools/ncu_traffic.py), or None when the capture is of another
+    workload or of other kernel sources (stale)."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_match_traffic.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_match_traffic.json")))
     except (OSError, ValueError):
         return None
-    if t.get("workload") == workload and t.get("particles") == nLocal:
+    if t.get("workload") == workload and t.get("particles") == nLocal and t.get("kernel_sha256") == kernel_source_hash():
         return t.get("dram_bytes_per_launch")
     return None
 
@@ -178,21 +196,12 @@ def run_b200(args):
     spec = synthetic.config(args.workload)
     nLocal = args.particles or spec["N"]
     K, W = args.steps, args.warmup
-    scene = synthetic.make_scene(seed=0, steps=1 + 2 * (K + W), K=spec["K"], fov=spec["og"][4], unit=spec["og"][3])
     np.random.seed(1234)                                  # same stream on every rank (sharding is invisible)
     spf = ShardedParticleFilter(nLocal * world, spec["og"], spec["sm"], device=dev)
     pf = spf.local
     pf.keepTrajectory = False
-    # maps pre-warmed with 8 scans at true poses, identical for all particles
-    og = S.OccupancyGrid(*pf.geom.args, _geometry=pf.geom)
-    for fr in scene["warm"]:
-        og.updateOccupancyGrid(fr)
-    pf.grids.copy_(og.device_grid.unsqueeze(0).expand_as(pf.grids))
-    del og
-    frames = scene["frames"]
-    spf.updateParticles(frames[0], 1)
-    spf.weightUnbalanced()
-    count = 1
+    pf.ignoreMissingHeading = True      # ~1e5 sampled particle-steps: the reference's None + float TypeError (a particle that
+                                        # did not move before a > 0.3 m odometry step) does occur; keep going like the kernels do
     geomBytes = pf.grids.numel() * 4
 
     def sync_all():
@@ -200,6 +209,50 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize(dev)
+
+    def fresh_scene(steps):
+        """Maps pre-warmed with 8 scans at true poses, identical for all particles; first reading consumed."""
+        scene = synthetic.make_scene(seed=0, steps=steps + 2, K=spec["K"], fov=spec["og"][4], unit=spec["og"][3],
+                                     stride=STRIDE)
+        return scene["frames"]
+
+    og = S.OccupancyGrid(*pf.geom.args, _geometry=pf.geom)
+    for fr in synthetic.make_scene(seed=0, steps=1, K=spec["K"], fov=spec["og"][4], unit=spec["og"][3],
+                                   stride=STRIDE)["warm"]:
+        og.updateOccupancyGrid(fr)
+    pf.grids.copy_(og.device_grid.unsqueeze(0).expand_as(pf.grids))
+    del og
+
+    # ---- pilot: a few steps through the public API to size the timed regions (>= MIN_TIMED_S each)
+    frames = fresh_scene(8 + 3 * (W + K))
+    count = 0
+    for fr in frames[:3]:
+        count += 1
+        spf.updateParticles(fr, count)
+        spf.weightUnbalanced()
+    sync_all()
+    t0 = time.perf_counter()
+    for fr in frames[3:6]:
+        count += 1
+        spf.updateParticles(fr, count)
+        spf.weightUnbalanced()
+    sync_all()
+    pilot = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(pilot, op=dist.ReduceOp.MAX)
+    repeats = max(1, int(np.ceil(MIN_TIMED_S / (float(pilot.item()) * K))))
+    KT = K * repeats                                      # timed steps per region
+
+    # The K-step schedule is replayed `repeats` times.  A replay starts from the same particle poses / headings /
+    # weights (the lattices keep integrating the scans): the reference never resamples a power-of-two population
+    # (SURVEY A9), so hundreds of consecutive sampled steps would only measure a diverging random walk.
+    def snapshot():
+        return (pf.prevMatched.clone(), pf.prevHeading.clone(), pf.hasHeading.clone(), pf.weights.clone(),
+                list(pf._prevRaw), list(pf._prevRawHeading))
+
+    def restore(sn):
+        pf.prevMatched.copy_(sn[0]); pf.prevHeading.copy_(sn[1]); pf.hasHeading.copy_(sn[2]); pf.weights.copy_(sn[3])
+        pf._prevRaw, pf._prevRawHeading = list(sn[4]), list(sn[5])
 
     # ---- (1) inputs resident in HBM: pre-stage every step's [ranges | uniforms | rv] row
     recs, rows = [], []
@@ -212,49 +265,71 @@ def run_b200(args):
         rec = pf._prepare(fr, count, nLocal, prevRaw, prevHead, out=row, uniforms=u)
         recs.append(rec); rows.append(row.to(dev))
         prevRaw, prevHead = fr, rec["newRawHeading"]
-    pf._prevRaw, pf._prevRawHeading = [prevRaw] * nLocal, [prevHead] * nLocal
+    mode1 = sum(1 for r in recs[W:] if r["mode"] == 1) * repeats
+    for i in range(W):
+        pf._launch(0, nLocal, recs[i], rows[i])
+        spf.gather_and_normalize()
+    snap = snapshot()
     sync_all()
-    launches0 = None
     with ClockSampler(local, rank == 0) as clk1:
-        for i in range(W + K):
-            if i == W:
-                sync_all()
-                pf.matchEvents = []
-                launches0 = pf.kernelLaunches
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(torch.cuda.current_stream(dev))
-            pf._launch(0, nLocal, recs[i], rows[i])
-            spf.gather_and_normalize()
+        pf.matchEvents = []
+        launches0 = pf.kernelLaunches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(dev))
+        for r in range(repeats):
+            restore(snap)
+            for i in range(W, W + K):
+                pf._launch(0, nLocal, recs[i], rows[i])
+                spf.gather_and_normalize()
         e1.record(torch.cuda.current_stream(dev))
         sync_all()
-    launches = pf.kernelLaunches - launches0
+    pf._prevRaw, pf._prevRawHeading = [prevRaw] * nLocal, [prevHead] * nLocal
+    launches = (pf.kernelLaunches - launches0) // repeats            # per K steps
     ms_dev = e0.elapsed_time(e1)
     matchMs = [a.elapsed_time(b) for a, b in pf.matchEvents]
     pf.matchEvents = None
-    st = int(pf.status.max().item())      # sticky OR-ed status words: any non-zero word has a bit set
+    st = int(torch.bitwise_and(pf.status, ~16).max().item())      # sticky OR-ed status words (HEADING_MISSING tolerated, see above)
     if st:
         raise RuntimeError("status bits %d set during the timed run" % st)
 
     # ---- (2) end to end through the public API with host readings
-    def api_step():
+    def api_step(fr):
         nonlocal count
         count += 1
-        spf.updateParticles(frames[count - 1], count)
+        spf.updateParticles(fr, count)
         return spf.weightUnbalanced()
-    for _ in range(W):
-        api_step()
+    base = count
+    for fr in frames[base:base + W]:
+        api_step(fr)
+    snap = snapshot()
     sync_all()
     h0, d0 = pf.h2dBytes, pf.d2hBytes
     with ClockSampler(local, rank == 0) as clk2:
         t0 = time.perf_counter()
-        for _ in range(K):
-            api_step()
+        for r in range(repeats):
+            restore(snap)
+            for fr in frames[base + W:base + W + K]:
+                api_step(fr)
         sync_all()
         t_e2e = time.perf_counter() - t0
-    h2d, d2h = (pf.h2dBytes - h0) // K, (pf.d2hBytes - d0) // K
+    h2d, d2h = (pf.h2dBytes - h0) // KT, (pf.d2hBytes - d0) // KT
+
+    # ---- (3) per-kernel breakdown: a few more steps with CUDA events around every launch (not part of the timings)
+    pf.timer.enabled = True
+    restore(snap)
+    for fr in frames[base + W:base + W + min(K, 8)]:
+        api_step(fr)
+    kernel_ms = pf.timer.mean_ms()
+    pf.timer.enabled = False
+
+    sharding = None
+    if world > 1:
+        from slam_2d_lidar_scan_b200.distributed import sharding_self_check
+        sharding = "pass" if sharding_self_check(dev) else "fail"
 
     # max over ranks
     t = torch.tensor([ms_dev, t_e2e * 1e3, statistics.mean(matchMs)], dtype=torch.float64, device=dev)
+    K = KT                                                # everything below is per timed step
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e, ms_match = (float(v) for v in t.cpu())
@@ -272,26 +347,30 @@ def run_b200(args):
         achieved = nLocal * bmatch / (ms_match * 1e-3) / 1e9
         c1, c2 = clk1.summary(), clk2.summary()
         out = {
-            "metric": METRIC, "value": total * K / (ms_dev * 1e-3), "unit": "particle-scans/s",
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True,
+            "impl": "b200", "metric": METRIC, "value": total * K / (ms_dev * 1e-3), "unit": "particle-scans/s",
+            "n_gpus": world, "steps": args.steps, "warmup": W, "repeats": repeats, "timed_steps": KT, "ms_per_step": ms_dev / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "particles_per_gpu": nLocal, "particles_total": total,
                        "beams": spec["K"], "grid": "%dx%d @%.2f m" % (pf.geom.G, pf.geom.G, pf.geom.unitGridSize),
                        "poses_per_scan": sum(int(np.prod(eng.volume_shape(s))) for s in (0, 1)),
                        "parallelism": "particles sharded, %d/GPU" % nLocal,
                        "l2": "inputs larger than L2 (%.1f GB of lattices per GPU vs 126 MB L2)" % (geomBytes / 1e9),
-                       "scene": "synthetic room seed 0 (SURVEY 8d), maps pre-warmed with 8 scans"},
+                       "scene": "synthetic room seed 0 (SURVEY 8d), maps pre-warmed with 8 scans, odometry step "
+                                "%.2f m (heading prior active in %d of %d timed steps)" % (STRIDE, mode1, KT)},
             "e2e": {"value": total * K / (ms_e2e * 1e-3), "unit": "particle-scans/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "kernel_ms": {k: round(v, 5) for k, v in sorted(kernel_ms.items())},
             "roofline": {"bound": "hbm", "kernel": "slam::match_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args.workload, nLocal),
                          "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_launch": nLocal * bmatch, "ms_per_launch": ms_match,
                          "share_of_step": ms_match / (ms_dev / K)},
             "clocks": {"sm_mhz": c1["sm_mhz"], "sm_max_mhz": c1["sm_max_mhz"],
-                       "reasons": sorted(set(c1["reasons"]) | set(c2["reasons"])), "e2e_sm_mhz": c2["sm_mhz"]},
+                       "reasons": sorted(set(c1["reasons"]) | set(c2["reasons"])), "e2e_sm_mhz": c2["sm_mhz"],
+                       "samples": c1.get("samples")},
         }
+        if sharding is not None:
+            out["sharding_check"] = sharding
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"], _ = cpu_baseline(args.workload, steps=args.cpu_steps)
         print(json.dumps(out), flush=True)
@@ -307,7 +386,8 @@ def _ref_init(workload, seed_base):
     """Pool initializer: every worker process owns one oracle particle, maps pre-warmed, first reading consumed."""
     from oracle import slam_oracle as O
     spec = importlib_pkg().synthetic.config(workload)
-    scene = importlib_pkg().synthetic.make_scene(seed=0, steps=70, K=spec["K"], fov=spec["og"][4], unit=spec["og"][3])
+    scene = importlib_pkg().synthetic.make_scene(seed=0, steps=70, K=spec["K"], fov=spec["og"][4], unit=spec["og"][3],
+                                                 stride=STRIDE)
     np.random.seed(seed_base + os.getpid() % 1000)
     p = O.Particle(spec["og"], spec["sm"])
     for fr in scene["warm"]:
@@ -382,6 +462,14 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and "RANK" not in os.environ:        # plain `python bench.py --gpus N`: start the N ranks ourselves
+        port = 29500 + os.getpid() % 2000
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if "RANK" in os.environ and world != args.gpus:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE is %d" % (args.gpus, world))
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -136,6 +136,14 @@ int slam_match_scan(slam_matcher* m, const float* d_grid, int32_t N, const doubl
                     int32_t* d_status, void* d_workspace, size_t workspaceBytes,
                     const slam_match_debug* debug, void* stream);
 
+/* The same with a slot table: particle p reads lattice d_slots[p] of the numLattices lattices at d_grid (NULL =
+ * identity).  Everything else (poses, priors, outputs, status) stays indexed by particle. */
+int slam_match_scan_slots(slam_matcher* m, const float* d_grid, const int32_t* d_slots, int32_t numLattices, int32_t N,
+                          const double* d_ranges, const double* d_estPose, const double* d_rv, const double* d_tw,
+                          const double* d_uniforms, double* d_outPose, double* d_outConf, int32_t* d_outIdx,
+                          int32_t* d_status, void* d_workspace, size_t workspaceBytes, const slam_match_debug* debug,
+                          void* stream);
+
 /* Heading prior thetaWeight (ScanMatcher_OGBased.py:105-108) for N particles:
  * tw[p][a][b] = coef * acos((xv*cos(phi_p) + yv*sin(phi_p)) / dist)^2, zeros where hasPhi[p] == 0.
  * coef = -1 / (2*turnSigma**2) evaluated by the host. */
@@ -152,6 +160,11 @@ int slam_update_grid(const slam_geometry* geom, float* d_grid, int32_t N, const 
                      const double* d_pose, int32_t* d_status, void* d_workspace, size_t workspaceBytes, void* stream);
 /* Device scratch slam_update_grid needs for N particles (per call; may be shared by calls on one stream). */
 size_t slam_update_workspace_bytes(int32_t N);
+/* The same with a slot table: particle p lives in lattice d_slots[p] of d_grid (NULL = identity).  Copy-elided
+ * resampling (slam_copy_lattices) permutes ownership of the lattices instead of moving them. */
+int slam_update_grid_slots(const slam_geometry* geom, float* d_grid, const int32_t* d_slots, int32_t N,
+                           const double* d_ranges, const double* d_pose, int32_t* d_status, void* d_workspace,
+                           size_t workspaceBytes, void* stream);
 
 /* Per-particle odometry proposal (FastSlam.py:77-106).  The raw-odometry part is identical for every
  * particle and is computed by the host: estTheta = (prevMatched.theta + rawTheta) - prevRawTheta (left to
@@ -182,6 +195,12 @@ int slam_status_reduce(int32_t N, const int32_t* d_status, int32_t* d_out, void*
  * d_cdfScratch [N] double. */
 int slam_resample_indices(int32_t N, const double* d_weights, const double* d_uniforms, double* d_cdfScratch,
                           int32_t* d_idx, void* stream);
+
+/* In-place lattice copies of a copy-elided resample (FastSlam.py:50-62 deep-copies every chosen particle; here only
+ * the extra copies of multiply-chosen particles move): lattice d_dst[c] := lattice d_src[c], c < nCopies.  Sources
+ * and destinations are disjoint sets of lattices (a source survives under its own slot). */
+int slam_copy_lattices(const slam_geometry* geom, float* d_grid, int32_t nCopies, const int32_t* d_src,
+                       const int32_t* d_dst, void* stream);
 
 /* dst particle i := src particle idx[i] for the lattices and the per-particle state rows
  * (deepcopy loop, FastSlam.py:60-62); weights := 1/N.  src and dst must not alias. */

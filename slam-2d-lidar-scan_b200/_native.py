@@ -59,6 +59,10 @@ SYMBOLS = {
     "slam_grid_init": (C.c_int, [C.POINTER(Geometry), _V, _I, _V]),
     "slam_update_grid": (C.c_int, [C.POINTER(Geometry), _V, _I, _V, _V, _V, _V, _Z, _V]),
     "slam_update_workspace_bytes": (_Z, [_I]),
+    "slam_update_grid_slots": (C.c_int, [C.POINTER(Geometry), _V, _V, _I, _V, _V, _V, _V, _Z, _V]),
+    "slam_match_scan_slots": (C.c_int, [_V, _V, _V, _I, _I, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _Z,
+                                        C.POINTER(MatchDebug), _V]),
+    "slam_copy_lattices": (C.c_int, [C.POINTER(Geometry), _V, _I, _V, _V, _V]),
     "slam_propose_poses": (C.c_int, [_I, _V, _D, _D, _I, _D, _V, _V, _V, _V, _V, _V, _V]),
     "slam_finish_step": (C.c_int, [_I, _V, _V, _V, _V, _V, _V, _V]),
     "slam_normalize_weights": (C.c_int, [_I, _V, _V, _V]),

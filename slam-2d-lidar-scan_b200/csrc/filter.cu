@@ -134,6 +134,15 @@ __global__ void gather_grid_kernel(const float4* src, float4* dst, const int* id
     d[k] = s[k];
 }
 
+// in-place copies of a copy-elided resample: lattice dst[c] := lattice src[c] (disjoint sets), 16-byte vectors
+__global__ void copy_lattice_kernel(float4* grid, const int* src, const int* dst, size_t n4PerParticle) {
+  const int c = blockIdx.y;
+  const float4* s = grid + (size_t)src[c] * n4PerParticle;
+  float4* d = grid + (size_t)dst[c] * n4PerParticle;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n4PerParticle; k += (size_t)gridDim.x * blockDim.x)
+    d[k] = __ldcs(s + k);
+}
+
 __global__ void gather_state_kernel(int N, const int* idx, const double* src, double* dst, int cols, double* weights) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= N) return;
@@ -210,5 +219,19 @@ extern "C" int slam_gather_particles(const slam_geometry* g, int32_t N, const in
     gather_state_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, d_idx, nullptr, nullptr, 0, d_weights);
   }
   SLAM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int slam_copy_lattices(const slam_geometry* g, float* d_grid, int32_t nCopies, const int32_t* d_src,
+                                  const int32_t* d_dst, void* stream) {
+  if (nCopies <= 0) return 0;
+  if (!g || !d_grid || !d_src || !d_dst) return fail(SLAM_E_BADARG, "slam_copy_lattices: bad argument");
+  const size_t n4 = (size_t)g->G * g->pitch / 2;
+  for (int32_t c0 = 0; c0 < nCopies; c0 += 65535) {          // gridDim.y limit
+    const int32_t nc = nCopies - c0 < 65535 ? nCopies - c0 : 65535;
+    dim3 grid(64, nc);
+    copy_lattice_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((float4*)d_grid, d_src + c0, d_dst + c0, n4);
+    SLAM_CUDA(cudaGetLastError());
+  }
   return 0;
 }

@@ -93,6 +93,7 @@ struct MatchParams {
   const double *gridX, *gridY;
   StageDev st[2];
   const float* grid;
+  const int* slots;      // physical lattice of particle p (null: p itself); see slam_copy_lattices
   const double *ranges, *estPose, *rv, *tw, *uniforms;
   double *outPose, *outConf;
   int *outIdx, *status;
@@ -1037,7 +1038,7 @@ __device__ __noinline__ void stream_role(const MatchParams& P, const CUtensorMap
   const int nMine = (P.N - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   long long* cyc = (P.dbgCycles && threadIdx.x == 0) ? P.dbgCycles + (size_t)blockIdx.x * 48 : nullptr;   // [7] TMA wait, [14] pack, [15] bitmap wait
   // producer cursor (warp-uniform): particle kP, own chunk cP (counts this warp's chunks), window wP
-  int kP = 0, cP = 0, nChP = -1, wP[4] = {0, 0, 0, 0};
+  int kP = 0, cP = 0, nChP = -1, latP = 0, wP[4] = {0, 0, 0, 0};
   unsigned issued = 0, consumed = 0;
   auto my_chunks = [&](int rows) { const int n = (rows + BY - 1) / BY; return n > sw ? (n - sw + NSW - 1) / NSW : 0; };
   auto top_up = [&]() {
@@ -1045,6 +1046,7 @@ __device__ __noinline__ void stream_role(const MatchParams& P, const CUtensorMap
       const int pP = (int)blockIdx.x + kP * (int)gridDim.x;
       if (nChP < 0) {
         union_window(P, pP, wP);
+        latP = P.slots ? P.slots[pP] : pP;
         nChP = my_chunks(kP == 0 ? first_rows_by_stream(wP[2], BY) : wP[2]);
         cP = 0;
       }
@@ -1054,7 +1056,7 @@ __device__ __noinline__ void stream_role(const MatchParams& P, const CUtensorMap
         const unsigned bar = smem_u32(&sh.ringFull[sw * RING_PER_WARP + st]);
         mbar_expect_tx(bar, stageBytes);
         for (int j = 0; j < nB; ++j)
-          tma_load_3d(ring + st * stageBytes + j * boxBytes, tmap, bar, wP[1] + j * BX, wP[0] + (sw + cP * NSW) * BY, pP);
+          tma_load_3d(ring + st * stageBytes + j * boxBytes, tmap, bar, wP[1] + j * BX, wP[0] + (sw + cP * NSW) * BY, latP);
       }
       ++issued; ++cP;
     }
@@ -1760,7 +1762,8 @@ __device__ __noinline__ void cold_start(const MatchParams& P) {
     union_window(P, p, w);
     const int r0 = first_rows_by_stream(w[2], P.ringRows);
     const int nTW = P.UWcells / 64, UW = P.UW, nc = w[3];
-    const float2* base = reinterpret_cast<const float2*>(P.grid) + ((size_t)p * P.G + w[0]) * P.pitch + w[1];
+    const size_t lat = P.slots ? P.slots[p] : p;
+    const float2* base = reinterpret_cast<const float2*>(P.grid) + (lat * P.G + w[0]) * P.pitch + w[1];
     for (int row = r0 + warp; row < w[2]; row += NWC) {
       const float2* src = base + (size_t)row * P.pitch;
       unsigned* Urow = Ubuf0 + (size_t)row * UW;
@@ -2211,13 +2214,23 @@ extern "C" int slam_match_scan(slam_matcher* m, const float* d_grid, int32_t N, 
                                const double* d_uniforms, double* d_outPose, double* d_outConf, int32_t* d_outIdx,
                                int32_t* d_status, void* d_workspace, size_t workspaceBytes,
                                const slam_match_debug* debug, void* stream) {
+  return slam_match_scan_slots(m, d_grid, nullptr, N, N, d_ranges, d_estPose, d_rv, d_tw, d_uniforms, d_outPose, d_outConf,
+                               d_outIdx, d_status, d_workspace, workspaceBytes, debug, stream);
+}
+
+extern "C" int slam_match_scan_slots(slam_matcher* m, const float* d_grid, const int32_t* d_slots, int32_t numLattices,
+                                     int32_t N, const double* d_ranges, const double* d_estPose, const double* d_rv,
+                                     const double* d_tw, const double* d_uniforms, double* d_outPose, double* d_outConf,
+                                     int32_t* d_outIdx, int32_t* d_status, void* d_workspace, size_t workspaceBytes,
+                                     const slam_match_debug* debug, void* stream) {
+  if (numLattices < N && !d_slots) return fail(SLAM_E_BADARG, "slam_match_scan_slots: fewer lattices than particles");
   if (!m || !d_grid || !d_ranges || !d_estPose || !d_rv || !d_outPose || !d_outConf || !d_outIdx || !d_status)
     return fail(SLAM_E_BADARG, "slam_match_scan: null argument");
   if (N <= 0) return 0;
   if (!d_workspace || workspaceBytes < m->workspaceBytes) return fail(SLAM_E_BADARG, "slam_match_scan: workspace too small");
   MatchParams P = m->P;
   P.N = N;
-  P.grid = d_grid; P.ranges = d_ranges; P.estPose = d_estPose; P.rv = d_rv; P.tw = d_tw; P.uniforms = d_uniforms;
+  P.grid = d_grid; P.slots = d_slots; P.ranges = d_ranges; P.estPose = d_estPose; P.rv = d_rv; P.tw = d_tw; P.uniforms = d_uniforms;
   P.outPose = d_outPose; P.outConf = d_outConf; P.outIdx = d_outIdx; P.status = d_status;
   P.scratch = (unsigned char*)align_up((size_t)d_workspace, 256);
   for (int s = 0; s < 2; ++s) {
@@ -2240,7 +2253,7 @@ extern "C" int slam_match_scan(slam_matcher* m, const float* d_grid, int32_t N, 
     m->attrSet = true;
   }
   // TMA descriptor of the lattice batch: [N][G][pitch] cells of 8 bytes, box = boxCells x ringRows x 1
-  if (m->tmapGrid != (const void*)d_grid || m->tmapN != N) {
+  if (m->tmapGrid != (const void*)d_grid || m->tmapN != numLattices) {
     if (!m->encode) {
       void* fn = nullptr;
       cudaDriverEntryPointQueryResult qres;
@@ -2248,7 +2261,7 @@ extern "C" int slam_match_scan(slam_matcher* m, const float* d_grid, int32_t N, 
       if (!fn || qres != cudaDriverEntryPointSuccess) return fail(SLAM_E_UNSUPPORTED, "cuTensorMapEncodeTiled is not available in this driver");
       m->encode = (EncodeTiledFn)fn;
     }
-    const cuuint64_t dims[3] = {(cuuint64_t)P.pitch, (cuuint64_t)P.G, (cuuint64_t)N};
+    const cuuint64_t dims[3] = {(cuuint64_t)P.pitch, (cuuint64_t)P.G, (cuuint64_t)numLattices};
     const cuuint64_t strides[2] = {(cuuint64_t)P.pitch * 8, (cuuint64_t)P.pitch * 8 * (cuuint64_t)P.G};
     const cuuint32_t box[3] = {(cuuint32_t)P.boxCells, (cuuint32_t)P.ringRows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
@@ -2257,7 +2270,7 @@ extern "C" int slam_match_scan(slam_matcher* m, const float* d_grid, int32_t N, 
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) return fail(SLAM_E_UNSUPPORTED, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)rc) + ")");
     m->tmapGrid = d_grid;
-    m->tmapN = N;
+    m->tmapN = numLattices;
   }
   const int grid = std::min(N, m->numCtas);
   match_kernel<<<grid, NT_ALL, m->smemBytes, (cudaStream_t)stream>>>(P, m->tmap);

@@ -26,13 +26,33 @@ struct UpdParams {
   int4* prep;   // per particle: (shiftX, shiftY, spokeOffset, flags) flags: bit0 pure shift
   int* slow;    // slow[0] = number of particles needing the general path, slow[1..] = their indices
   int* status;
+  const int* slots;   // physical lattice of particle p (null: p itself) -- copy-elided resampling keeps a slot table
+  double* reach;      // [1] largest radius any beam of this scan can touch (empty or hit), written by the prep kernel
 };
+
+__device__ __forceinline__ size_t lattice_of(const UpdParams& P, int p) { return (size_t)(P.slots ? P.slots[p] : p); }
 
 constexpr int UPD_PURE = 1;
 
 // one warp per particle: float64 index maps of the local lattice (OccupancyGrid.py:144-145 via :102-106)
 __global__ void update_prep_kernel(UpdParams P) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x >= blockDim.x - 32) {
+    // last warp of the grid (spare by construction): the largest cell radius this scan can touch.  A beam empties
+    // r < range - wall/2 (only if range < maxRange) and hits range - wall/2 < r < range + wall/2; the patch holds no
+    // cell beyond sqrt(2) * maxRange, so a beam whose hit band starts past that (the log's 81.83 m sentinel) hits none.
+    const double patchR = dmul(1.4143, P.maxRange);
+    double reach = 0.0;
+    for (int k = lane; k < P.K; k += 32) {
+      const double rm = P.ranges[k], lo = dsub(rm, P.wallHalf), hi = dadd(rm, P.wallHalf);
+      if (rm < P.maxRange) reach = fmax(reach, lo);
+      if (lo < patchR) reach = fmax(reach, hi);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) reach = fmax(reach, __shfl_xor_sync(0xffffffffu, reach, d));
+    if (lane == 0) P.reach[0] = reach;
+    return;
+  }
   if (warp >= P.N) return;
   const double x = P.pose[3 * warp], y = P.pose[3 * warp + 1], th = P.pose[3 * warp + 2];
   const int sx = (int)rint(ddiv(dsub(dadd(x, P.axis[0]), P.mapX0), P.unit));
@@ -81,13 +101,34 @@ __global__ void __launch_bounds__(256) update_fast_kernel(UpdParams P) {
     }
     s_loE[k] = loE; s_lo[k] = lo; s_hi[k] = hi;
   }
-  if (threadIdx.x < np) s_prep[threadIdx.x] = P.prep[p0 + threadIdx.x];
+  __shared__ size_t s_lat[UPD_CHUNK];
+  __shared__ int s_fan[2];      // sectors any particle of the chunk can look at: [start, start + length) mod numSpokes
+  if (threadIdx.x < np) {
+    s_prep[threadIdx.x] = P.prep[p0 + threadIdx.x];
+    s_lat[threadIdx.x] = lattice_of(P, p0 + threadIdx.x);
+  }
+  if (threadIdx.x < 32) {       // headings of a chunk differ by a few spokes: union of the particles' beam fans
+    const int nS = P.numSpokes, ref = P.prep[p0].z;
+    int d = 0;
+    if ((int)threadIdx.x < np) {
+      d = P.prep[p0 + threadIdx.x].z - ref;
+      d = ((d + nS / 2) % nS + nS) % nS - nS / 2;      // signed circular distance to the first particle's shift
+    }
+    const int dmin = __reduce_min_sync(0xffffffffu, d), dmax = __reduce_max_sync(0xffffffffu, d);
+    if (threadIdx.x == 0) { s_fan[0] = ((ref + dmin) % nS + nS) % nS; s_fan[1] = P.K + (dmax - dmin); }
+  }
   __syncthreads();
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= P.L * P.L) return;
   const int ly = cell / P.L, lx = cell - ly * P.L;
   const int sec = P.sector[cell];
+  {   // cells no particle of the chunk can touch: outside the union of the fans, or beyond the reach of the scan
+    int rel = sec - s_fan[0];
+    if (rel < 0) rel += P.numSpokes;
+    if (rel >= s_fan[1]) return;
+  }
   const double r = P.radius[cell];
+  if (!(r < P.reach[0])) return;
   const size_t gstride = (size_t)P.G * P.pitch;
   int bad = 0;
   // particles of the chunk in groups of 8: all reads of a group are issued before its writes (distinct particles
@@ -111,7 +152,7 @@ __global__ void __launch_bounds__(256) update_fast_kernel(UpdParams P) {
             if (jx < 0 || jy < 0 || jx >= P.G || jy >= P.G) bad = 1;
             else {
               flag[j] = f;
-              ptr[j] = (float2*)P.grid + (size_t)(p0 + q) * gstride + (size_t)jy * P.pitch + jx;
+              ptr[j] = (float2*)P.grid + s_lat[q] * gstride + (size_t)jy * P.pitch + jx;
             }
           }
         }
@@ -195,7 +236,7 @@ __device__ void update_general_one(const UpdParams& P, int p, int* mx, int* my) 
     if (flag[k] & 2) { dv += 2.f; dt += 2.f; }
   }
   if (jx < 0 || jy < 0 || jx >= P.G || jy >= P.G) { atomicOr(&P.status[p], SLAM_ST_SCAN_OUTSIDE_MAP); return; }
-  float2* c = (float2*)P.grid + (size_t)p * P.G * P.pitch + (size_t)jy * P.pitch + jx;
+  float2* c = (float2*)P.grid + lattice_of(P, p) * P.G * P.pitch + (size_t)jy * P.pitch + jx;
   float2 v = *c;
   v.x += dv; v.y += dt;
   *c = v;
@@ -224,12 +265,18 @@ extern "C" int slam_grid_init(const slam_geometry* g, float* d_grid, int32_t N, 
 static size_t upd_prep_bytes(int32_t N) { return ((size_t)N * sizeof(int4) + 255) / 256 * 256; }
 
 extern "C" size_t slam_update_workspace_bytes(int32_t N) {
-  return N <= 0 ? 0 : upd_prep_bytes(N) + ((size_t)N + 1) * sizeof(int) + 256;
+  return N <= 0 ? 0 : upd_prep_bytes(N) + 256 + ((size_t)N + 1) * sizeof(int) + 256;
 }
 
 extern "C" int slam_update_grid(const slam_geometry* g, float* d_grid, int32_t N, const double* d_ranges,
                                 const double* d_pose, int32_t* d_status, void* d_workspace, size_t workspaceBytes,
                                 void* stream) {
+  return slam_update_grid_slots(g, d_grid, nullptr, N, d_ranges, d_pose, d_status, d_workspace, workspaceBytes, stream);
+}
+
+extern "C" int slam_update_grid_slots(const slam_geometry* g, float* d_grid, const int32_t* d_slots, int32_t N,
+                                      const double* d_ranges, const double* d_pose, int32_t* d_status, void* d_workspace,
+                                      size_t workspaceBytes, void* stream) {
   if (!g || !d_grid || !d_ranges || !d_pose || !d_status) return fail(SLAM_E_BADARG, "slam_update_grid: null argument");
   if (N <= 0) return 0;
   if (g->K > SLAM_MAX_BEAMS) return fail(SLAM_E_UNSUPPORTED, "too many beams");
@@ -241,14 +288,15 @@ extern "C" int slam_update_grid(const slam_geometry* g, float* d_grid, int32_t N
   const size_t prepBytes = upd_prep_bytes(N);
   unsigned char* scratch = (unsigned char*)(((size_t)d_workspace + 255) / 256 * 256);
   int4* g_prep = reinterpret_cast<int4*>(scratch);
-  int* g_slow = reinterpret_cast<int*>(scratch + prepBytes);
+  double* g_reach = reinterpret_cast<double*>(scratch + prepBytes);
+  int* g_slow = reinterpret_cast<int*>(scratch + prepBytes + 256);
   SLAM_CUDA(cudaMemsetAsync(g_slow, 0, sizeof(int), st));
   UpdParams P;
   P.G = g->G; P.pitch = g->pitch; P.K = g->K; P.L = g->L; P.numSpokes = g->numSpokes; P.start = g->spokesStartIdx; P.N = N;
   P.unit = g->unit; P.mapX0 = g->mapX0; P.mapY0 = g->mapY0; P.maxRange = g->maxRange; P.wallHalf = g->wallHalf;
   P.sector = g->d_sector; P.radius = g->d_radius; P.axis = g->d_localAxis; P.ranges = d_ranges; P.pose = d_pose;
-  P.grid = d_grid; P.prep = g_prep; P.slow = g_slow; P.status = d_status;
-  update_prep_kernel<<<(N * 32 + 255) / 256, 256, 0, st>>>(P);
+  P.grid = d_grid; P.prep = g_prep; P.slow = g_slow; P.status = d_status; P.slots = d_slots; P.reach = g_reach;
+  update_prep_kernel<<<((N + 1) * 32 + 255) / 256, 256, 0, st>>>(P);      // + 1: the warp that computes the scan's reach
   SLAM_CUDA(cudaGetLastError());
   {
     dim3 grid((g->L * g->L + 255) / 256, (N + UPD_CHUNK - 1) / UPD_CHUNK);

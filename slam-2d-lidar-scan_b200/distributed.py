@@ -14,7 +14,7 @@ import torch
 import torch.distributed as dist
 
 from . import _native as nat
-from .engine import StepResult, raise_for_status, _stream
+from .engine import StepResult, raise_for_status, copy_lattices, _stream
 from .fastslam import ParticleFilter
 
 
@@ -94,6 +94,8 @@ class ShardedParticleFilter:
         self.gather_and_normalize()
         var, fired, bits = self._res.fetch()
         self.local.d2hBytes += 24
+        if self.local.ignoreMissingHeading:
+            bits &= ~nat.ST_HEADING_MISSING
         raise_for_status(bits)
         self.lastVariance = var
         return fired
@@ -103,7 +105,10 @@ class ShardedParticleFilter:
         return self._all[:, :self.hi - self.lo, 1:].reshape(-1, 3).cpu().numpy()
 
     def resample(self):
-        """Global multinomial resample (FastSlam.py:50-62); lattices whose source lives on another rank move P2P."""
+        """Global multinomial resample (FastSlam.py:50-62).  Lattices whose source lives on another rank move
+        point-to-point into staging buffers; locally, ownership of a chosen particle's lattice is handed over through
+        the slot table and only the extra copies of multiply-chosen particles are physically copied
+        (engine.plan_copy_elided).  Per-particle state and trajectory history travel with the particle."""
         pf, n, nL = self.local, self.numParticles, self.hi - self.lo
         dev = pf.geom.device
         u = torch.from_numpy(np.random.random_sample(n)).to(dev)                  # same draw on every rank
@@ -111,29 +116,103 @@ class ShardedParticleFilter:
                                                 self._ridx.data_ptr(), _stream(dev)))
         idx = self._ridx.cpu().numpy()
         plan = plan_resample_transfers(idx, nL, self.world)[self.rank]
-        state = torch.cat([pf.prevMatched, pf.prevHeading.view(-1, 1), pf.hasHeading.to(torch.float64).view(-1, 1)], 1)
-        newGrids, newState = torch.empty_like(pf.grids), torch.empty_like(state)
-        for d, s in plan["local"]:
-            newGrids[d].copy_(pf.grids[s])
-            newState[d].copy_(state[s])
+        hist = torch.stack(pf._traj, 0) if pf._traj else None                    # [T][nL][2] matched positions so far
+        cols = [pf.prevMatched, pf.prevHeading.view(-1, 1), pf.hasHeading.to(torch.float64).view(-1, 1)]
+        if hist is not None:
+            cols.append(hist.permute(1, 0, 2).reshape(nL, -1))
+        state = torch.cat(cols, 1).contiguous()
+        newState = torch.empty_like(state)
+        # remote sources: lattices arrive in staging buffers (their final lattice may still be a send source)
+        staging = {d: torch.empty_like(pf.grids[0]) for _, d, _ in plan["recvs"]}
         ops = []
-        for dstRank, s, tag in plan["sends"]:
-            ops.append(dist.P2POp(dist.isend, pf.grids[s], dstRank, group=self.group))
-            ops.append(dist.P2POp(dist.isend, state[s], dstRank, group=self.group))
+        for dstRank, sLoc, tag in plan["sends"]:
+            ops.append(dist.P2POp(dist.isend, pf.lattice(sLoc), dstRank, group=self.group))
+            ops.append(dist.P2POp(dist.isend, state[sLoc], dstRank, group=self.group))
         for srcRank, d, tag in plan["recvs"]:
-            ops.append(dist.P2POp(dist.irecv, newGrids[d], srcRank, group=self.group))
+            ops.append(dist.P2POp(dist.irecv, staging[d], srcRank, group=self.group))
             ops.append(dist.P2POp(dist.irecv, newState[d], srcRank, group=self.group))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
-        pf.grids.copy_(newGrids)
-        del newGrids
-        pf.prevMatched.copy_(newState[:, :3])
-        pf.prevHeading.copy_(newState[:, 3])
-        pf.hasHeading.copy_(newState[:, 4].to(torch.int32))
+        # local part: new local particle d <- old local particle s (ownership hand-over / elided copies); destinations
+        # with a remote source take the lattices nobody (locally) chose
+        local = dict(plan["local"])                                              # dstLocal -> srcLocal
+        taken = np.zeros(nL, dtype=bool)
+        newSlots = np.empty(nL, dtype=np.int32)
+        extra, copies = [], []
+        for d in range(nL):
+            sLoc = local.get(d)
+            if sLoc is not None and not taken[sLoc]:
+                taken[sLoc] = True
+                newSlots[d] = pf._slots_h[sLoc]
+            else:
+                extra.append(d)
+            if sLoc is not None:
+                newState[d].copy_(state[sLoc])
+        free = list(pf._slots_h[~taken])
+        for d, f in zip(extra, free):
+            newSlots[d] = f
+            if d in staging:
+                pf.grids[int(f)].copy_(staging[d])
+            else:
+                copies.append((int(pf._slots_h[local[d]]), int(f)))
+        copy_lattices(pf.geom, pf.grids, copies)
+        pf._slots_h = newSlots
+        pf.slots.copy_(torch.from_numpy(newSlots))
+        pf.resampleCopies += len(copies) + len(staging)
+        pf.lastResampleCopies = len(copies) + len(staging)
+        pf.prevMatched = newState[:, :3].contiguous()
+        pf.prevHeading = newState[:, 3].contiguous()
+        pf.hasHeading = newState[:, 4].to(torch.int32).contiguous()
+        if hist is not None:
+            pf._traj = list(newState[:, 5:].reshape(nL, hist.shape[0], 2).permute(1, 0, 2).contiguous().unbind(0))
         pf.weights.fill_(1.0 / n)
         src = [int(idx[i]) for i in range(self.lo, self.hi)]
-        # trajectories / raw-odometry records are identical host data on every rank except per-particle history
-        pf._traj = []           # per-particle history does not follow a particle across ranks (documented)
         self.lastResampleIdx = idx.astype(np.int64)
         return src
+
+
+def sharding_self_check(dev, steps=9, perRank=8, workload="c2", seed=77):
+    """Sharding must be invisible in the results: every rank runs the sharded filter (perRank particles per rank, one
+    all-gather per step, one forced cross-rank resample) and then the unsharded filter with the same seed on its own
+    GPU; poses, weights, trigger decisions, resample indices and the rank's lattices must agree bit for bit on every
+    rank.  Collective (call on all ranks); returns the global verdict."""
+    from . import synthetic
+    from .grid import OccupancyGrid
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    spec = synthetic.config(workload)
+    N = perRank * world
+    scene = synthetic.make_scene(seed=1, steps=steps, K=spec["K"], fov=spec["og"][4], unit=spec["og"][3])
+
+    def run(cls):
+        np.random.seed(seed)
+        pf = cls(N, spec["og"], spec["sm"], device=dev)
+        loc = pf.local if hasattr(pf, "local") else pf
+        og = OccupancyGrid(*loc.geom.args, _geometry=loc.geom)
+        for fr in scene["warm"]:
+            og.updateOccupancyGrid(fr)
+        loc.load_grid(og.device_grid)
+        log = []
+        for count, fr in enumerate(scene["frames"][:steps], start=1):
+            pf.updateParticles(fr, count)
+            fired = pf.weightUnbalanced()
+            w = (pf._w if hasattr(pf, "local") else pf.weights).cpu().numpy().copy()
+            log.append((fired, pf.poses().copy(), w))
+            if count == 6:                       # force a resample to exercise the cross-rank lattice moves
+                pf.resample()
+        return pf, log
+
+    state = np.random.get_state()
+    try:
+        spf, a = run(ShardedParticleFilter)
+        ref, b = run(ParticleFilter)
+    finally:
+        np.random.set_state(state)
+    ok = all(fa == fb and np.array_equal(pa, pb) and np.array_equal(wa, wb) for (fa, pa, wa), (fb, pb, wb) in zip(a, b))
+    ok = ok and np.array_equal(spf.lastResampleIdx, ref.lastResampleIdx)
+    for i in range(spf.lo, spf.hi):              # lattices after the forced resample + 3 more steps
+        ok = ok and bool(torch.equal(spf.local.lattice(i - spf.lo), ref.lattice(i)))
+    t = torch.tensor([1 if ok else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return int(t.item()) == 1

@@ -149,13 +149,15 @@ class MatcherEngine:
         return dbg, bufs
 
     def match(self, grids, n, d_ranges, d_estPose, d_rv, d_tw, d_uniforms, d_outPose, d_outConf, d_outIdx, d_status,
-              debug=None):
+              debug=None, slots=None):
         """slam_match_scan on the geometry's device, current stream.  All arguments are device tensors (or None).
-        Status bits are OR-ed into d_status (sticky)."""
+        Status bits are OR-ed into d_status (sticky).  ``slots`` (int32 [n]): particle p reads lattice slots[p] of
+        ``grids`` (all lattices of the filter) instead of lattice p."""
         dev = self.geom.device
         with torch.cuda.device(dev):
-            nat.check(nat.lib.slam_match_scan(
-                self.handle, grids.data_ptr(), n, d_ranges.data_ptr(), d_estPose.data_ptr(), d_rv.data_ptr(), _ptr(d_tw),
+            nat.check(nat.lib.slam_match_scan_slots(
+                self.handle, grids.data_ptr(), _ptr(slots), grids.shape[0] if slots is not None else n, n,
+                d_ranges.data_ptr(), d_estPose.data_ptr(), d_rv.data_ptr(), _ptr(d_tw),
                 _ptr(d_uniforms), d_outPose.data_ptr(), d_outConf.data_ptr(), d_outIdx.data_ptr(), d_status.data_ptr(),
                 self.workspace.data_ptr(), self.workspace.numel(), C.byref(debug) if debug is not None else None,
                 _stream(dev)))
@@ -165,11 +167,50 @@ class MatcherEngine:
         return (len(self.stageInfo[stage]["thetas"]), n, n)
 
 
-def update_grids(geom, grids, n, d_ranges, d_pose, d_status):
+def update_grids(geom, grids, n, d_ranges, d_pose, d_status, slots=None):
     ws = geom.update_workspace(n)
     with torch.cuda.device(geom.device):
-        nat.check(nat.lib.slam_update_grid(geom.c, grids.data_ptr(), n, d_ranges.data_ptr(), d_pose.data_ptr(),
-                                           d_status.data_ptr(), ws.data_ptr(), ws.numel(), _stream(geom.device)))
+        nat.check(nat.lib.slam_update_grid_slots(geom.c, grids.data_ptr(), _ptr(slots), n, d_ranges.data_ptr(),
+                                                 d_pose.data_ptr(), d_status.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                 _stream(geom.device)))
+
+
+def plan_copy_elided(idx, slots):
+    """Copy-elided resample (FastSlam.py:50-62 deep-copies every chosen particle).  idx[i] = old particle the new
+    particle i is a copy of, slots[p] = lattice that holds old particle p.  The first new particle that chooses p
+    simply takes over p's lattice; only the further copies of a multiply-chosen particle are physically copied, into
+    the lattices of particles nobody chose.  -> (newSlots[i], [(srcLattice, dstLattice), ...]) with
+    len(copies) == N - (number of distinct chosen particles)."""
+    idx = np.asarray(idx, dtype=np.int64)
+    slots = np.asarray(slots, dtype=np.int64)
+    n = len(idx)
+    newSlots = np.empty(n, dtype=np.int32)
+    taken = np.zeros(n, dtype=bool)
+    extra = []
+    for i in range(n):
+        s = idx[i]
+        if not taken[s]:
+            taken[s] = True
+            newSlots[i] = slots[s]
+        else:
+            extra.append(i)
+    free = slots[~taken]
+    copies = []
+    for i, f in zip(extra, free):
+        newSlots[i] = f
+        copies.append((int(slots[idx[i]]), int(f)))
+    return newSlots, copies
+
+
+def copy_lattices(geom, grids, copies):
+    """slam_copy_lattices for a list of (srcLattice, dstLattice) pairs."""
+    if not copies:
+        return
+    dev = geom.device
+    pairs = torch.tensor(copies, dtype=torch.int32).t().contiguous().to(dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib.slam_copy_lattices(geom.c, grids.data_ptr(), len(copies), pairs[0].data_ptr(),
+                                             pairs[1].data_ptr(), _stream(dev)))
 
 
 class StepResult:

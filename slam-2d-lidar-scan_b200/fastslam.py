@@ -15,10 +15,43 @@ import numpy as np
 import torch
 
 from . import _native as nat
-from .engine import MatcherEngine, StepResult, raise_for_status, update_grids, _stream
+from .engine import (MatcherEngine, StepResult, raise_for_status, update_grids, plan_copy_elided, copy_lattices,
+                     _stream)
 from .geometry import LidarGeometry
 from .grid import OccupancyGrid
 from .matcher import ScanMatcher
+
+
+class KernelTimer:
+    """CUDA-event timing of the individual kernel launches of a step (bench.py's per-kernel breakdown).  Disabled
+    (the default) it costs one attribute test per launch."""
+
+    def __init__(self):
+        self.enabled = False
+        self.events = {}
+
+    def section(self, name, dev):
+        return _Section(self, name, dev)
+
+    def mean_ms(self):
+        torch.cuda.synchronize()
+        return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in self.events.items() if v}
+
+
+class _Section:
+    def __init__(self, timer, name, dev):
+        self.t, self.name, self.dev = timer, name, dev
+
+    def __enter__(self):
+        if self.t.enabled:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream(self.dev))
+
+    def __exit__(self, *a):
+        if self.t.enabled:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(torch.cuda.current_stream(self.dev))
+            self.t.events.setdefault(self.name, []).append((self.e0, e1))
 
 
 class Particle:
@@ -26,7 +59,8 @@ class Particle:
 
     def __init__(self, pf, i):
         self._pf, self._i = pf, i
-        self.og = OccupancyGrid(*pf.geom.args, _geometry=pf.geom, _grids=pf.grids, _slot=i)
+        self.og = OccupancyGrid(*pf.geom.args, _geometry=pf.geom, _grids=pf.grids, _slot=i,
+                                _slotmap=lambda: pf._slots_h)
         self.sm = ScanMatcher(self.og, *pf.smParameters, _engine=pf.engine)
 
     @property
@@ -86,6 +120,10 @@ class ParticleFilter:
         f64 = dict(dtype=torch.float64, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
         self.grids = self.geom.new_grids(n)
+        # particle -> lattice table: resampling hands lattices over instead of copying them (plan_copy_elided)
+        self._slots_h = np.arange(n, dtype=np.int32)
+        self.slots = torch.arange(n, dtype=torch.int32, device=dev)
+        self.resampleCopies = 0              # lattices physically copied by resample() so far
         self.prevMatched = torch.zeros((n, 3), **f64)
         self.prevHeading = torch.zeros(n, **f64)
         self.hasHeading = torch.zeros(n, **i32)
@@ -113,6 +151,10 @@ class ParticleFilter:
         self.keepTrajectory = True           # per-step [N][2] device copy of the matched positions
         self.kernelLaunches = 0              # kernels of this library enqueued so far
         self.matchEvents = None              # list -> (start, end) CUDA events around every match launch
+        self.timer = KernelTimer()           # per-kernel CUDA events when .enabled
+        # The reference dies with a TypeError (None + float, FastSlam.py:96) when a particle did not move in the step
+        # before a > 0.3 m odometry step; True = carry on with a zero heading prior for that particle instead.
+        self.ignoreMissingHeading = False
         self.h2dBytes = 0
         self.d2hBytes = 0
         self._prevRaw = [None] * n
@@ -147,6 +189,8 @@ class ParticleFilter:
         self.kernelLaunches += 1
         var, fired, bits = self._res.fetch()
         self.d2hBytes += 24
+        if self.ignoreMissingHeading:
+            bits &= ~nat.ST_HEADING_MISSING
         raise_for_status(bits)
         self.lastVariance = var
         return fired
@@ -158,26 +202,36 @@ class ParticleFilter:
         st = _stream(dev)
         nat.check(nat.lib.slam_resample_indices(n, self.weights.data_ptr(), u.data_ptr(), self._cdf.data_ptr(),
                                                 self._ridx.data_ptr(), st))
-        newGrids = torch.empty_like(self.grids)
-        newPrev = torch.empty_like(self.prevMatched)
-        nat.check(nat.lib.slam_gather_particles(self.geom.c, n, self._ridx.data_ptr(), self.grids.data_ptr(),
-                                                newGrids.data_ptr(), self.prevMatched.data_ptr(), newPrev.data_ptr(),
-                                                3, self.weights.data_ptr(), st))
         idx = self._ridx.to(torch.int64)
-        self.grids.copy_(newGrids)                 # keep the storage the Particle views alias
-        self.prevMatched.copy_(newPrev)
-        del newGrids
+        hidx = idx.cpu().tolist()
+        # lattices: ownership moves with the slot table; only the extra copies of multiply-chosen particles are copied
+        newSlots, copies = plan_copy_elided(hidx, self._slots_h)
+        copy_lattices(self.geom, self.grids, copies)
+        self._slots_h = newSlots
+        self.slots.copy_(torch.from_numpy(newSlots))
+        self.resampleCopies += len(copies)
+        self.lastResampleCopies = len(copies)
+        # small per-particle state: plain gathers in particle order
+        self.prevMatched = self.prevMatched.index_select(0, idx).contiguous()
         self.prevHeading = self.prevHeading.index_select(0, idx).contiguous()
         self.hasHeading = self.hasHeading.index_select(0, idx).contiguous()
+        self.weights.fill_(1.0 / n)                                      # :62 (1 / numParticles)
         self._traj = [t.index_select(0, idx) for t in self._traj]
-        hidx = idx.cpu().tolist()
         self._prevRaw = [self._prevRaw[i] for i in hidx]
         self._prevRawHeading = [self._prevRawHeading[i] for i in hidx]
         self.lastResampleIdx = np.asarray(hidx)
 
+    def lattice(self, i):
+        """[G][pitch][2] device view of particle i's (visited, total) lattice."""
+        return self.grids[int(self._slots_h[i])]
+
+    def load_grid(self, grid):
+        """Every particle's map := ``grid`` ([G][pitch][2] float32)."""
+        self.grids.copy_(grid.unsqueeze(0).expand_as(self.grids))
+
     # ---- device step
     def _normalize(self):
-        with torch.cuda.device(self.geom.device):
+        with torch.cuda.device(self.geom.device), self.timer.section("normalize_kernel", self.geom.device):
             nat.check(nat.lib.slam_normalize_weights(self.numParticles, self.weights.data_ptr(), self._out.data_ptr(),
                                                      _stream(self.geom.device)))
         self.kernelLaunches += 1
@@ -227,28 +281,32 @@ class ParticleFilter:
         else:
             d_u = d_stage[K:K + n]
             d_rv = d_stage[K + N:K + N + n2]
-            nat.check(nat.lib.slam_propose_poses(
-                n, self.prevMatched[lo:hi].data_ptr(), rec["rawTheta"], rec["prevRawTheta"], rec["mode"],
-                rec["rawTurn"], self.prevHeading[lo:hi].data_ptr(), self.hasHeading[lo:hi].data_ptr(),
-                self._est[lo:hi].data_ptr(), self._phi[lo:hi].data_ptr(), self._hasPhi[lo:hi].data_ptr(),
-                status.data_ptr(), st))
+            with self.timer.section("propose_kernel", dev):
+                nat.check(nat.lib.slam_propose_poses(
+                    n, self.prevMatched[lo:hi].data_ptr(), rec["rawTheta"], rec["prevRawTheta"], rec["mode"],
+                    rec["rawTurn"], self.prevHeading[lo:hi].data_ptr(), self.hasHeading[lo:hi].data_ptr(),
+                    self._est[lo:hi].data_ptr(), self._phi[lo:hi].data_ptr(), self._hasPhi[lo:hi].data_ptr(),
+                    status.data_ptr(), st))
             tw = None
             if rec["mode"] == 1:
                 tw = self._tw[lo:hi]
-                nat.check(nat.lib.slam_motion_priors(n, eng.stageInfo[0]["nHalf"], eng.heading_coef,
-                                                     self._phi[lo:hi].data_ptr(), self._hasPhi[lo:hi].data_ptr(),
-                                                     tw.data_ptr(), st))
+                with self.timer.section("priors_kernel", dev):
+                    nat.check(nat.lib.slam_motion_priors(n, eng.stageInfo[0]["nHalf"], eng.heading_coef,
+                                                         self._phi[lo:hi].data_ptr(), self._hasPhi[lo:hi].data_ptr(),
+                                                         tw.data_ptr(), st))
             if self.matchEvents is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record(torch.cuda.current_stream(dev))
-            eng.match(self.grids[lo:hi], n, d_stage[:K], self._est[lo:hi], d_rv, tw, d_u, matched,
-                      self._conf[lo:hi], self._idx[lo:hi], status)
+            with self.timer.section("match_kernel", dev):
+                eng.match(self.grids, n, d_stage[:K], self._est[lo:hi], d_rv, tw, d_u, matched,
+                          self._conf[lo:hi], self._idx[lo:hi], status, slots=self.slots[lo:hi])
             if self.matchEvents is not None:
                 ev1.record(torch.cuda.current_stream(dev))
                 self.matchEvents.append((ev0, ev1))
-            nat.check(nat.lib.slam_finish_step(n, matched.data_ptr(), self._conf[lo:hi].data_ptr(),
-                                               self.prevMatched[lo:hi].data_ptr(), self.prevHeading[lo:hi].data_ptr(),
-                                               self.hasHeading[lo:hi].data_ptr(), self.weights[lo:hi].data_ptr(), st))
+            with self.timer.section("finish_kernel", dev):
+                nat.check(nat.lib.slam_finish_step(n, matched.data_ptr(), self._conf[lo:hi].data_ptr(),
+                                                   self.prevMatched[lo:hi].data_ptr(), self.prevHeading[lo:hi].data_ptr(),
+                                                   self.hasHeading[lo:hi].data_ptr(), self.weights[lo:hi].data_ptr(), st))
         if self.keepTrajectory:
             if n == N:
                 self._traj.append(matched[:, :2].clone())
@@ -257,7 +315,8 @@ class ParticleFilter:
                     self._traj.append(torch.zeros((N, 2), dtype=torch.float64, device=dev))
                 self._traj[-1][lo:hi] = matched[:, :2]
             self._trajCount = count
-        update_grids(self.geom, self.grids[lo:hi], n, d_stage[:K], matched, status)           # :133
+        with self.timer.section("update_kernels", dev):
+            update_grids(self.geom, self.grids, n, d_stage[:K], matched, status, slots=self.slots[lo:hi])    # :133
         self.kernelLaunches += 3 + (0 if count == 1 else 3 + (1 if rec["mode"] == 1 else 0))
 
     def _update(self, lo, hi, reading, count, uniforms=None):

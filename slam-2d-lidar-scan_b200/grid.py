@@ -10,12 +10,13 @@ from .geometry import LidarGeometry
 
 class OccupancyGrid:
     def __init__(self, mapXLength, mapYLength, initXY, unitGridSize, lidarFOV, numSamplesPerRev, lidarMaxRange,
-                 wallThickness, *, device=None, _geometry=None, _grids=None, _slot=0):
+                 wallThickness, *, device=None, _geometry=None, _grids=None, _slot=0, _slotmap=None):
         self.geom = _geometry or LidarGeometry(mapXLength, mapYLength, initXY, unitGridSize, lidarFOV,
                                                numSamplesPerRev, lidarMaxRange, wallThickness, device=device)
         g = self.geom
         self._grids = g.new_grids(1) if _grids is None else _grids      # [N][G][pitch][2] float32
         self._slot = _slot
+        self._slotmap = _slotmap          # particle -> lattice table of the owning filter (copy-elided resampling)
         self.unitGridSize = g.unitGridSize
         self.lidarFOV = g.lidarFOV
         self.lidarMaxRange = g.lidarMaxRange
@@ -35,7 +36,7 @@ class OccupancyGrid:
     @property
     def device_grid(self):
         """[G][pitch][2] float32 view of this map's (visited, total) counts."""
-        return self._grids[self._slot]
+        return self._grids[self._slot if self._slotmap is None else int(self._slotmap()[self._slot])]
 
     def _counts(self, ch):
         return self.device_grid[:, :self.geom.G, ch].to(torch.float64).cpu().numpy()

@@ -44,16 +44,17 @@ def _cast(segs, x, y, angles):
     return t.min(axis=1)
 
 
-def make_scene(seed=0, steps=64, K=180, fov=np.pi, unit=0.05, origin=(0.0, 0.0), warm=8):
+def make_scene(seed=0, steps=64, K=180, fov=np.pi, unit=0.05, origin=(0.0, 0.0), warm=8, stride=0.25):
     """Returns dict(frames=[reading...], warm=[reading...], truth=[(x,y,theta)...]).
 
     ``warm`` readings carry TRUE poses snapped to the map lattice (origin + k*unit) and are meant for pre-warming
     the maps with updateOccupancyGrid; ``frames`` carry noisy odometry poses and are fed to the filter.
+    ``stride`` is the arc length per step: above 0.3 m the reference's heading prior is active (FastSlam.py:88).
     """
     rng = np.random.default_rng(seed)
     segs = _segments(rng)
     total = warm + steps
-    dphi = 0.25 / 3.0
+    dphi = stride / 3.0
     truth, scans = [], []
     for k in range(total):
         phi = dphi * k

@@ -194,9 +194,15 @@ def test_resample_copies_particles_like_the_oracle(S, frames):
             if count == 6:
                 log.append(pf.poses() if hasattr(pf, "poses") else _poses(pf))
                 pf.resample()
+                if hasattr(pf, "lastResampleCopies"):       # copy elision: only the extra duplicates move (F2)
+                    assert pf.lastResampleCopies == 6 - len(set(int(v) for v in pf.lastResampleIdx))
                 log.append(np.array(pf.lastResampleIdx))
                 log.append([p.weight for p in pf.particles])
                 log.append([p.og.occupancyGridTotal.copy() for p in pf.particles])
+            if count == 8:
+                pf.resample()
+                log.append(np.array(pf.lastResampleIdx))
+        log.append([p.og.occupancyGridVisited.copy() for p in pf.particles])
         log.append(pf.poses() if hasattr(pf, "poses") else _poses(pf))
         log.append(np.random.random_sample())
         return log

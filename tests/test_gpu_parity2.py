@@ -244,3 +244,20 @@ def test_translation_by_whole_cells_shifts_the_result(S, frames):
         outs.append((idxs, np.array(poses), og.occupancyGridTotal.copy()))
     assert outs[0][0] == outs[1][0]
     assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+
+
+@pytest.mark.gpu
+def test_sharding_is_invisible_across_two_gpus():
+    """Two ranks (NCCL) vs the unsharded filter, bit for bit, incl. a forced cross-rank resample.
+    Needs two GPUs on the box; skipped otherwise."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29400 + os.getpid() % 500
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(root, "tools", "check_sharded.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SHARDED_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
