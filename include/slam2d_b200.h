@@ -144,6 +144,32 @@ int slam_match_scan_slots(slam_matcher* m, const float* d_grid, const int32_t* d
                           int32_t* d_status, void* d_workspace, size_t workspaceBytes, const slam_match_debug* debug,
                           void* stream);
 
+/*
+ * Stage-level entry points: the reference's public stage methods, for callers that drive the stages themselves
+ * (slam_match_scan fuses them and keeps the fields on chip).
+ *
+ * slam_field_build   <- ScanMatcher.frameSearchSpace (:20-39) incl. generateProbSearchSpace (:41-45): the clamped
+ *   likelihood field of `stage` (0 coarse, 1 fine) around d_centre[p] = (x, y, -); d_prob [N][side*side] with row pitch
+ *   side = slam_matcher_field_side(stage), d_probDims [N][2] = (rows, cols) used.  xRangeList / yRangeList are
+ *   centre -+ windowRadius (host arithmetic).
+ * slam_correlate     <- ScanMatcher.searchToMatch (:91-151) against a caller-provided field of the same layout:
+ *   d_centre [N][3] pose, d_origin [N][2] = (xRangeList[0], yRangeList[0]), d_rv / d_tw priors (NULL = zeros, the
+ *   fineSearch=True case), d_uniforms NULL -> matchMax=True else the double np.random.choice draws;
+ *   d_vol [N][nPoses] convTotal, d_outIdx [N][3] (itheta, iy, ix), d_outConf [N] = sum(exp(convTotal)).
+ *   Workspace: min(N, SMs) * nPoses * 8 bytes (+512).
+ * slam_blur_clamp    <- ScanMatcher.generateProbSearchSpace (:41-45) on an arbitrary float64 array: scipy's
+ *   gaussian_filter (taps d_taps[2*radius+1], reflect borders, axis 0 then 1), min, clamp.  d_tmp: rows*cols doubles.
+ */
+int slam_field_build(slam_matcher* m, int32_t stage, const float* d_grid, int32_t N, const double* d_centre,
+                     double* d_prob, int32_t* d_probDims, int32_t* d_status, void* d_workspace, size_t workspaceBytes,
+                     void* stream);
+int slam_correlate(slam_matcher* m, int32_t stage, int32_t N, const double* d_prob, const int32_t* d_probDims,
+                   const double* d_ranges, const double* d_centre, const double* d_origin, const double* d_rv,
+                   const double* d_tw, const double* d_uniforms, double* d_vol, int32_t* d_outIdx, double* d_outConf,
+                   int32_t* d_status, void* d_workspace, size_t workspaceBytes, void* stream);
+int slam_blur_clamp(const double* d_in, int32_t rows, int32_t cols, const double* d_taps, int32_t radius, double* d_tmp,
+                    double* d_out, void* stream);
+
 /* Heading prior thetaWeight (ScanMatcher_OGBased.py:105-108) for N particles:
  * tw[p][a][b] = coef * acos((xv*cos(phi_p) + yv*sin(phi_p)) / dist)^2, zeros where hasPhi[p] == 0.
  * coef = -1 / (2*turnSigma**2) evaluated by the host. */

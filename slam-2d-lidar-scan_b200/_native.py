@@ -63,6 +63,9 @@ SYMBOLS = {
     "slam_match_scan_slots": (C.c_int, [_V, _V, _V, _I, _I, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _Z,
                                         C.POINTER(MatchDebug), _V]),
     "slam_copy_lattices": (C.c_int, [C.POINTER(Geometry), _V, _I, _V, _V, _V]),
+    "slam_field_build": (C.c_int, [_V, _I, _V, _I, _V, _V, _V, _V, _V, _Z, _V]),
+    "slam_correlate": (C.c_int, [_V, _I, _I, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _Z, _V]),
+    "slam_blur_clamp": (C.c_int, [_V, _I, _I, _V, _I, _V, _V, _V]),
     "slam_propose_poses": (C.c_int, [_I, _V, _D, _D, _I, _D, _V, _V, _V, _V, _V, _V, _V]),
     "slam_finish_step": (C.c_int, [_I, _V, _V, _V, _V, _V, _V, _V]),
     "slam_normalize_weights": (C.c_int, [_I, _V, _V, _V]),

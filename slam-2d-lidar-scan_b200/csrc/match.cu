@@ -103,6 +103,7 @@ struct MatchParams {
   int* dbgDims[2];
   double* dbgVol[2];
   long long* dbgCycles;  // [gridDim][48] or null
+  int fieldOnlyStage;    // -1: the whole matchScan; 0 / 1: only build (and dump) that stage's likelihood field around estPose
   int forceExactCdf;
   int forceGenericScatter;   // test hook: always take the atomicOr scatter path
   int noPrune;               // test hook: evaluate every fine hypothesis completely (no branch-and-bound)
@@ -446,6 +447,15 @@ __device__ __forceinline__ void build_list(const double* dxs, const double* dys,
   }
   int total = __shfl_sync(FULL, incl, 31);
   if (lane == 0) *cnt = total;
+}
+
+// numpy's argmax order: the first maximum in C order, and a NaN beats every number (np.argmax returns the first NaN)
+__device__ __forceinline__ bool first_max_better(double v, int i, double b, int bi) {
+  if (i < 0) return false;
+  if (bi < 0) return true;
+  const bool vn = v != v, bn = b != b;
+  if (vn || bn) return vn && (!bn || i < bi);
+  return v > b || (v == b && i < bi);
 }
 
 struct BlockScratch {
@@ -892,7 +902,7 @@ __device__ __noinline__ void score_batch(const ScoreArgs& A) {
         if (scores) scores[flat] = v;
         if (A.dvol) A.dvol[flat] = v;
         if (v != v) sawNan = 1;
-        if (bestIdx < 0 || v > best || (v == best && flat < bestIdx)) { best = v; bestIdx = flat; }
+        if (first_max_better(v, flat, best, bestIdx)) { best = v; bestIdx = flat; }
         if (PRUNE && v > lds_f64(A.bestS)) {
           // scores are <= 0: the larger double has the smaller bit pattern
           atomicMin(reinterpret_cast<unsigned long long*>(A.bestP), (unsigned long long)__double_as_longlong(v));
@@ -905,14 +915,14 @@ __device__ __noinline__ void score_batch(const ScoreArgs& A) {
   for (int d = 16; d > 0; d >>= 1) {
     const double ob = __shfl_xor_sync(FULL, best, d);
     const int oi = __shfl_xor_sync(FULL, bestIdx, d);
-    if (oi >= 0 && (bestIdx < 0 || ob > best || (ob == best && oi < bestIdx))) { best = ob; bestIdx = oi; }
+    if (first_max_better(ob, oi, best, bestIdx)) { best = ob; bestIdx = oi; }
   }
   sawNan = __any_sync(FULL, sawNan);
   if ((tid & 31) == 0) {
     const int warp = tid >> 5;
     const double ob = A.bs->wbest[warp];
     const int oi = A.bs->wbestIdx[warp];
-    if (bestIdx >= 0 && (oi < 0 || best > ob || (best == ob && bestIdx < oi))) { A.bs->wbest[warp] = best; A.bs->wbestIdx[warp] = bestIdx; }
+    if (first_max_better(best, bestIdx, ob, oi)) { A.bs->wbest[warp] = best; A.bs->wbestIdx[warp] = bestIdx; }
     if (sawNan) A.bs->nanFlag = 1;
   }
 }
@@ -1157,7 +1167,8 @@ __device__ __noinline__ void window_phase(const MatchParams& P, CtaShared& sh, i
   const double cx = ctx.cx, cy = ctx.cy;
   const unsigned* U = reinterpret_cast<const unsigned*>(gslot + P.gU) + (size_t)(k & 1) * P.URows * P.UW;   // this particle's union bitmap
   const int* uwin = sh.uwin[k & 1];
-  const unsigned uEmptyBar = stageId == 1 ? smem_u32(&sh.ss.uEmpty[k & 1]) : 0u;     // the fine stage is its last reader
+  // the fine stage is the last reader of the union bitmap (or the only stage of a field-only call)
+  const unsigned uEmptyBar = (stageId == 1 || P.fieldOnlyStage == 0) ? smem_u32(&sh.ss.uEmpty[k & 1]) : 0u;
   // ---- A. geometry of the search window (ScanMatcher_OGBased.py:21-28)
   const double xr0 = dsub(cx, P.R), xr1 = dadd(cx, P.R);
   const double yr0 = dsub(cy, P.R), yr1 = dadd(cy, P.R);
@@ -1485,7 +1496,7 @@ __device__ __noinline__ void field_phase(const MatchParams& P, CtaShared& sh, in
   double* dys = sbuf<double>(S.oDy);
   int K0;
   {
-    const int K = P.K;
+    const int K = P.fieldOnlyStage >= 0 ? 0 : P.K;      // slam_field_build has no scan
     const double start = dsub(cth, P.fovHalf), stop = dadd(cth, P.fovHalf);
     const double step = ddiv(dsub(stop, start), (double)(K - 1));
     int base = 0;
@@ -1601,7 +1612,9 @@ __device__ __noinline__ void select_phase(const MatchParams& P, CtaShared& sh, i
   SubCyc sc;
   sc.start(sub);
   // ---- H. select (:133-141)
-  if (bs.nanFlag) status |= SLAM_ST_NAN_SCORE;      // (the correlate phase ended with a barrier)
+  // NaN scores: np.random.choice raises ValueError (:138); np.argmax just returns the first NaN (:134), so only the
+  // sampled stage reports them (the correlate phase ended with a barrier)
+  if (bs.nanFlag && sample) status |= SLAM_ST_NAN_SCORE;
   int chosen;
   {  // first maximum in C order: the per-warp maxima of the correlate phase
     double b = bs.wbest[0];
@@ -1609,7 +1622,7 @@ __device__ __noinline__ void select_phase(const MatchParams& P, CtaShared& sh, i
     for (int w2 = 1; w2 < NWC; ++w2) {
       double ob = bs.wbest[w2];
       int oi = bs.wbestIdx[w2];
-      if (oi >= 0 && (bi < 0 || ob > b || (ob == b && oi < bi))) { b = ob; bi = oi; }
+      if (first_max_better(ob, oi, b, bi)) { b = ob; bi = oi; }
     }
     chosen = bi;
     csync();
@@ -1739,12 +1752,13 @@ __device__ __forceinline__ void run_stage(const MatchParams& P, CtaShared& sh, i
   csync();                // the previous stage's readers of ctx are done, its result is published
   if (ctid() == 0) {
     StageCtx& ctx = sh.ctx;
-    if (stageId == 0) { ctx.cx = P.estPose[3 * p]; ctx.cy = P.estPose[3 * p + 1]; ctx.cth = P.estPose[3 * p + 2]; }
+    if (stageId == 0 || P.fieldOnlyStage >= 0) { ctx.cx = P.estPose[3 * p]; ctx.cy = P.estPose[3 * p + 1]; ctx.cth = P.estPose[3 * p + 2]; }
     else { ctx.cx = sh.res[0].x; ctx.cy = sh.res[0].y; ctx.cth = sh.res[0].th; }     // centred on the coarse result (:66-73)
   }
   csync();
   window_phase<FAST, DENSE>(P, sh, stageId, k, status);
   field_phase<FAST, DENSE>(P, sh, stageId, p, status);
+  if (P.fieldOnlyStage >= 0) return;      // slam_field_build: the field was dumped by field_phase
   correlate_phase<FAST, DENSE>(P, sh, stageId, p, status);
   select_phase<FAST, DENSE>(P, sh, stageId, p, status);
 }
@@ -1807,13 +1821,17 @@ __device__ __noinline__ void match_particle(const MatchParams& P, CtaShared& sh,
   csync();
   if (cyc && ctid() == 0) { const long long t = clock64(); cyc[6] += t; if (k == 0) cyc[28] += t; }
   if (P.fast) {      // everything but the sparse fine field lives in shared memory
-    run_stage<true, true>(P, sh, 0, p, k, status);
-    run_stage<true, false>(P, sh, 1, p, k, status);
+    if (P.fieldOnlyStage != 1) run_stage<true, true>(P, sh, 0, p, k, status);
+    if (P.fieldOnlyStage != 0) run_stage<true, false>(P, sh, 1, p, k, status);
   } else {           // large windows: bitmaps / fields / scores in the global slot
-    run_stage<false, false>(P, sh, 0, p, k, status);
-    run_stage<false, false>(P, sh, 1, p, k, status);
+    if (P.fieldOnlyStage != 1) run_stage<false, false>(P, sh, 0, p, k, status);
+    if (P.fieldOnlyStage != 0) run_stage<false, false>(P, sh, 1, p, k, status);
   }
   status = block_or(status, sh.bs);
+  if (P.fieldOnlyStage >= 0) {
+    if (ctid() == 0) P.status[p] |= status;
+    return;
+  }
   if (ctid() == 0) {
     const StageOut c = sh.res[0], f = sh.res[1];
     P.outPose[3 * p] = f.x; P.outPose[3 * p + 1] = f.y; P.outPose[3 * p + 2] = f.th;
@@ -1841,6 +1859,225 @@ __global__ void __launch_bounds__(NT_ALL, 1) match_kernel(const __grid_constant_
   if ((int)blockIdx.x < P.N) cold_start(P);
   int k = 0;
   for (int p = blockIdx.x; p < P.N; p += gridDim.x, ++k) match_particle(P, sh, p, k);
+}
+
+
+// ------------------------------------------------------------------------------------------------ stage-level entries
+// ScanMatcher.searchToMatch (:91-151) against a CALLER-PROVIDED dense likelihood field (the reference's public stage
+// API passes probSP between frameSearchSpace and searchToMatch).  One CTA walks over particles; not the hot path --
+// slam_match_scan keeps the field on chip -- but the same list / pairwise-sum / select code, so convTotal is bit-equal.
+struct CorrParams {
+  int N, K, stage, sampleMode;
+  double fovHalf, maxRange;
+  const double *prob;          // [N][probStride], row pitch probPitch
+  size_t probStride;
+  int probPitch;
+  const int* dims;             // [N][2] rows, cols
+  const double *ranges, *centre, *origin, *rv, *tw, *uniforms;
+  double *vol, *outConf;
+  int* outIdx;
+  int* status;
+  unsigned char* scratch;      // per CTA: nPoses doubles
+  size_t slotBytes;
+  int Kpad, oLists, oCnt, oDx, oDy, oLeaf, oRed;
+};
+
+struct FetchGlobalDense {
+  const unsigned* list;
+  const double* base;
+  unsigned off;
+  int pitch, two;
+  __device__ __forceinline__ void get(int k, double (&v)[GRP]) const {
+    const unsigned sxy = list[k] + off;
+    const double* q = base + (size_t)(sxy & 0xffffu) * pitch + (sxy >> 16);
+    v[0] = q[0];
+    v[1] = two ? q[1] : 0.0;
+  }
+};
+
+__global__ void __launch_bounds__(256) correlate_kernel(const __grid_constant__ CorrParams C, const __grid_constant__ StageDev S) {
+  __shared__ double s_bestV[8];
+  __shared__ int s_bestI[8], s_cnt[16], s_K0, s_status, s_chosen;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NWB = blockDim.x >> 5;
+  double* dxs = sbuf<double>(C.oDx);
+  double* dys = sbuf<double>(C.oDy);
+  unsigned* lists = sbuf<unsigned>(C.oLists);
+  int* cnts = sbuf<int>(C.oCnt);
+  double* leafSum = sbuf<double>(C.oLeaf);
+  double* e = reinterpret_cast<double*>(C.scratch + (size_t)blockIdx.x * C.slotBytes);
+  const int nOff = S.nOff, nOff2 = nOff * nOff, nPoses = S.nPoses;
+  const double ul = S.unitLength;
+  for (int p = blockIdx.x; p < C.N; p += gridDim.x) {
+    const double cx = C.centre[3 * p], cy = C.centre[3 * p + 1], cth = C.centre[3 * p + 2];
+    const double bx = C.origin[2 * p], by = C.origin[2 * p + 1];
+    const int Wy = C.dims[2 * p], Wx = C.dims[2 * p + 1];
+    int status = 0;
+    if (tid == 0) s_status = 0;
+    // beam end points (:81-89), order-preserving compaction of beams < maxRange
+    {
+      const double start = dsub(cth, C.fovHalf), stop = dadd(cth, C.fovHalf);
+      const double step = ddiv(dsub(stop, start), (double)(C.K - 1));
+      int base = 0;
+      for (int k0 = 0; k0 < C.K; k0 += blockDim.x) {
+        const int k = k0 + tid;
+        bool keep = false;
+        double ddx = 0, ddy = 0;
+        if (k < C.K) {
+          const double rm = C.ranges[k];
+          keep = rm < C.maxRange;
+          const double ang = (k == C.K - 1) ? stop : dadd(dmul((double)k, step), start);
+          double sn, cs;
+          sincos(ang, &sn, &cs);
+          const double px = dadd(cx, dmul(cs, rm)), py = dadd(cy, dmul(sn, rm));
+          ddx = dsub(px, cx); ddy = dsub(py, cy);
+        }
+        const unsigned bal = __ballot_sync(FULL, keep);
+        __syncthreads();
+        if (lane == 0) s_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int before = base, tot = 0;
+        for (int w2 = 0; w2 < NWB; ++w2) { if (w2 < warp) before += s_cnt[w2]; tot += s_cnt[w2]; }
+        if (keep) { const int pos = before + __popc(bal & ((1u << lane) - 1u)); dxs[pos] = ddx; dys[pos] = ddy; }
+        base += tot;
+      }
+      if (tid == 0) s_K0 = base;
+    }
+    __syncthreads();
+    const int K0 = s_K0;
+    for (int tl = warp; tl < S.nTheta; tl += NWB) {
+      if (S.E == 8) build_list<8>(dxs, dys, K0, cx, cy, S.cosT[tl], S.sinT[tl], bx, by, ul, S.nHalf, Wx, Wy, lists + tl * C.Kpad, cnts + tl, lane, status);
+      else build_list<16>(dxs, dys, K0, cx, cy, S.cosT[tl], S.sinT[tl], bx, by, ul, S.nHalf, Wx, Wy, lists + tl * C.Kpad, cnts + tl, lane, status);
+    }
+    __syncthreads();
+    // scores (:125-132)
+    const double* prob = C.prob + (size_t)p * C.probStride;
+    double* vol = C.vol + (size_t)p * nPoses;
+    const double* tw = C.tw ? C.tw + (size_t)p * nOff2 : nullptr;
+    const int nGrp = (nOff + GRP - 1) / GRP, perTheta = nOff * nGrp;
+    double best = 0.0;
+    int bestIdx = -1, sawNan = 0;
+    PruneCtx pc;
+    pc.bestS = 0u; pc.h1 = 0; pc.validMask = 0;
+    for (int q = tid; q < S.nTheta * perTheta; q += blockDim.x) {
+      const int tl = q / perTheta, rem0 = q - tl * perTheta;
+      const int a = rem0 / nGrp, b0 = (rem0 - a * nGrp) * GRP;
+      FetchGlobalDense f;
+      f.list = lists + tl * C.Kpad; f.base = prob; f.pitch = C.probPitch; f.two = b0 + 1 < nOff;
+      f.off = (unsigned)(((b0 - S.nHalf) << 16) + (a - S.nHalf));
+      double sc[GRP];
+      pairwise_g<false>(f, cnts[tl], sc, pc);
+      for (int g = 0; g < GRP; ++g) {
+        const int b = b0 + g;
+        if (b >= nOff) continue;
+        const int rem = a * nOff + b, flat = tl * nOff2 + rem;
+        double v = sc[g];
+        if (C.rv) v = dadd(v, C.rv[rem]);
+        if (tw) v = dadd(v, tw[rem]);
+        vol[flat] = v;
+        if (v != v) sawNan = 1;
+        if (first_max_better(v, flat, best, bestIdx)) { best = v; bestIdx = flat; }
+      }
+    }
+    // first maximum in C order
+    for (int d = 16; d > 0; d >>= 1) {
+      const double ob = __shfl_xor_sync(FULL, best, d);
+      const int oi = __shfl_xor_sync(FULL, bestIdx, d);
+      if (first_max_better(ob, oi, best, bestIdx)) { best = ob; bestIdx = oi; }
+    }
+    if (__any_sync(FULL, sawNan) && C.sampleMode) status |= SLAM_ST_NAN_SCORE;      // argmax: numpy returns the first NaN
+    if (lane == 0) { s_bestV[warp] = best; s_bestI[warp] = bestIdx; }
+    if (status) atomicOr(&s_status, status);
+    __syncthreads();
+    if (tid == 0) {
+      double b = s_bestV[0]; int bi = s_bestI[0];
+      for (int w2 = 1; w2 < NWB; ++w2) {
+        const double ob = s_bestV[w2]; const int oi = s_bestI[w2];
+        if (first_max_better(ob, oi, b, bi)) { b = ob; bi = oi; }
+      }
+      s_chosen = bi < 0 ? 0 : bi;
+    }
+    // confidence = np.sum(np.exp(convTotal)): numpy pairwise sum over the flattened volume (:141)
+    for (int i = tid; i < nPoses; i += blockDim.x) e[i] = exp(vol[i]);
+    __syncthreads();
+    for (int g0 = warp * 4; g0 < S.nLeaves; g0 += NWB * 4) {
+      const int g = g0 + (lane >> 3), l = lane & 7;
+      const bool valid = g < S.nLeaves;
+      const int2 lf = valid ? S.leaves[g] : make_int2(0, 0);
+      const int off = lf.x, n = lf.y, m = n - (n & 7);
+      double r = (n >= 8) ? e[off + l] : 0.0;
+      for (int i = 8; i < m; i += 8) r = dadd(r, e[off + i + l]);
+      r = dadd(r, __shfl_xor_sync(FULL, r, 1));
+      r = dadd(r, __shfl_xor_sync(FULL, r, 2));
+      r = dadd(r, __shfl_xor_sync(FULL, r, 4));
+      if (n < 8) r = 0.0;
+      for (int i = (n < 8 ? 0 : m); i < n; ++i) r = dadd(r, e[off + i]);
+      if (valid && l == 0) leafSum[g] = r;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int l = 0; l < S.nLevels; ++l) {
+        const int o1 = S.levelStart[l + 1];
+        for (int o = S.levelStart[l] + lane; o < o1; o += 32) {
+          const int2 op = S.ops[o];
+          leafSum[S.nLeaves + o] = dadd(leafSum[op.x], leafSum[op.y]);
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    const double conf = leafSum[S.nOps ? S.nLeaves + S.nOps - 1 : 0];
+    if (C.sampleMode) {   // np.random.choice (:137-139): p = e / e.sum(); cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, 'right')
+      for (int i = tid; i < nPoses; i += blockDim.x) e[i] = ddiv(e[i], conf);
+      __syncthreads();
+      if (tid == 0) {
+        const double u = C.uniforms[p];
+        double c = 0.0;
+        for (int i = 0; i < nPoses; ++i) c = dadd(c, e[i]);
+        const double last = c;
+        c = 0.0;
+        int found = nPoses;
+        for (int i = 0; i < nPoses; ++i) {
+          c = dadd(c, e[i]);
+          if (ddiv(c, last) > u) { found = i; break; }
+        }
+        s_chosen = min(found, nPoses - 1);
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      const int chosen = s_chosen, it = chosen / nOff2, rem = chosen - it * nOff2;
+      C.outIdx[3 * p] = it; C.outIdx[3 * p + 1] = rem / nOff; C.outIdx[3 * p + 2] = rem - (rem / nOff) * nOff;
+      C.outConf[p] = conf;
+      C.status[p] |= s_status;
+    }
+    __syncthreads();
+  }
+}
+
+// scipy.ndimage.gaussian_filter on an arbitrary float64 array (generateProbSearchSpace :41-45): one axis per launch,
+// reflect (half-sample symmetric) borders, out = x[c]*w[r]; out += (x[c+j] + x[c-j])*w[j+r], j = -r..-1.
+__global__ void blur_axis_kernel(const double* in, double* out, int rows, int cols, int axis, int r, const double* w) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * cols) return;
+  const int y = (int)(i / cols), x = (int)(i - (size_t)y * cols);
+  const int n = axis == 0 ? rows : cols, c = axis == 0 ? y : x;
+  auto at = [&](int k) { const int kk = reflect_idx(k, n); return axis == 0 ? in[(size_t)kk * cols + x] : in[(size_t)y * cols + kk]; };
+  double v = dmul(at(c), w[r]);
+  for (int j = -r; j < 0; ++j) v = dadd(v, dmul(dadd(at(c + j), at(c - j)), w[j + r]));
+  out[i] = v;
+}
+__global__ void min_kernel(const double* in, size_t n, double* out) {       // one block
+  __shared__ double s[32];
+  double v = INFINITY;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) v = fmin(v, in[i]);
+  for (int d = 16; d > 0; d >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, d));
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) { for (int k = 1; k < (int)(blockDim.x >> 5); ++k) v = fmin(v, s[k]); out[0] = v; }
+}
+__global__ void clamp_kernel(double* a, size_t n, const double* probMin) {   // probSP[probSP > 0.5 * probMin] = 0 (:44)
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && a[i] > dmul(0.5, probMin[0])) a[i] = 0.0;
 }
 
 // First-pass (axis 0) value for every occupancy pattern of a column's 2r+1 rows; same operation order as scipy:
@@ -2116,6 +2353,7 @@ extern "C" int slam_matcher_create(const slam_geometry* g, const slam_matcher_de
   slam_matcher* m = new slam_matcher();
   MatchParams& P = m->P;
   memset(&P, 0, sizeof(P));
+  P.fieldOnlyStage = -1;
   P.G = g->G; P.pitch = g->pitch; P.K = g->K;
   P.unit = g->unit; P.mapX0 = g->mapX0; P.mapX1 = g->mapX1; P.mapY0 = g->mapY0; P.mapY1 = g->mapY1;
   P.fovHalf = g->fovHalf; P.maxRange = g->maxRange; P.R = d->windowRadius;
@@ -2209,6 +2447,8 @@ extern "C" int slam_matcher_plan(const slam_matcher* m, int stage, int* out8) {
   return 0;
 }
 
+static int launch_match(slam_matcher* m, MatchParams& P, int numLattices, void* stream);
+
 extern "C" int slam_match_scan(slam_matcher* m, const float* d_grid, int32_t N, const double* d_ranges,
                                const double* d_estPose, const double* d_rv, const double* d_tw,
                                const double* d_uniforms, double* d_outPose, double* d_outConf, int32_t* d_outIdx,
@@ -2239,6 +2479,12 @@ extern "C" int slam_match_scan_slots(slam_matcher* m, const float* d_grid, const
     P.dbgVol[s] = debug ? debug->d_vol[s] : nullptr;
     if (P.dbgProb[s] && !P.dbgDims[s]) return fail(SLAM_E_BADARG, "d_prob needs d_probDims");
   }
+  return launch_match(m, P, numLattices, stream);
+}
+
+static int launch_match(slam_matcher* m, MatchParams& P, int numLattices, void* stream) {
+  const float* d_grid = P.grid;
+  const int N = P.N;
   int dev = 0;
   SLAM_CUDA(cudaGetDevice(&dev));
   if (dev != m->device) return fail(SLAM_E_BADARG, "slam_match_scan: the current device is not the one the matcher was created on");
@@ -2285,6 +2531,81 @@ extern "C" int slam_motion_priors(int32_t N, int32_t nHalf, double coef, const d
   const long long total = (long long)N * (2 * nHalf + 1) * (2 * nHalf + 1);
   const int bt = 256;
   priors_kernel<<<(unsigned)((total + bt - 1) / bt), bt, 0, (cudaStream_t)stream>>>(N, nHalf, coef, d_phi, d_hasPhi, d_tw);
+  SLAM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- stage-level entry points: the reference's public frameSearchSpace / searchToMatch /
+//      generateProbSearchSpace, for callers that drive the stages themselves
+extern "C" int slam_field_build(slam_matcher* m, int32_t stage, const float* d_grid, int32_t N, const double* d_centre,
+                                double* d_prob, int32_t* d_probDims, int32_t* d_status, void* d_workspace,
+                                size_t workspaceBytes, void* stream) {
+  if (!m || !d_grid || !d_centre || !d_prob || !d_probDims || !d_status || (stage != 0 && stage != 1))
+    return fail(SLAM_E_BADARG, "slam_field_build: bad argument");
+  if (N <= 0) return 0;
+  if (!d_workspace || workspaceBytes < m->workspaceBytes) return fail(SLAM_E_BADARG, "slam_field_build: workspace too small");
+  MatchParams P = m->P;
+  P.N = N;
+  P.fieldOnlyStage = stage;
+  P.grid = d_grid; P.slots = nullptr; P.estPose = d_centre; P.status = d_status;
+  P.ranges = nullptr; P.rv = nullptr; P.tw = nullptr; P.uniforms = nullptr;
+  P.outPose = nullptr; P.outConf = nullptr; P.outIdx = nullptr;
+  P.scratch = (unsigned char*)align_up((size_t)d_workspace, 256);
+  for (int s = 0; s < 2; ++s) { P.dbgProb[s] = nullptr; P.dbgDims[s] = nullptr; P.dbgVol[s] = nullptr; }
+  P.dbgProb[stage] = d_prob;
+  P.dbgDims[stage] = d_probDims;
+  P.dbgCycles = nullptr;
+  return launch_match(m, P, N, stream);
+}
+
+extern "C" int slam_correlate(slam_matcher* m, int32_t stage, int32_t N, const double* d_prob, const int32_t* d_probDims,
+                              const double* d_ranges, const double* d_centre, const double* d_origin, const double* d_rv,
+                              const double* d_tw, const double* d_uniforms, double* d_vol, int32_t* d_outIdx,
+                              double* d_outConf, int32_t* d_status, void* d_workspace, size_t workspaceBytes, void* stream) {
+  if (!m || !d_prob || !d_probDims || !d_ranges || !d_centre || !d_origin || !d_vol || !d_outIdx || !d_outConf || !d_status ||
+      (stage != 0 && stage != 1))
+    return fail(SLAM_E_BADARG, "slam_correlate: bad argument");
+  if (N <= 0) return 0;
+  const StageDev& S = m->P.st[stage];
+  CorrParams C;
+  memset(&C, 0, sizeof(C));
+  C.N = N; C.K = m->P.K; C.stage = stage; C.sampleMode = d_uniforms ? 1 : 0;
+  C.fovHalf = m->P.fovHalf; C.maxRange = m->P.maxRange;
+  C.prob = d_prob; C.probPitch = S.Wmax; C.probStride = (size_t)S.Wmax * S.Wmax; C.dims = d_probDims;
+  C.ranges = d_ranges; C.centre = d_centre; C.origin = d_origin; C.rv = d_rv; C.tw = d_tw; C.uniforms = d_uniforms;
+  C.vol = d_vol; C.outIdx = d_outIdx; C.outConf = d_outConf; C.status = d_status;
+  C.slotBytes = align_up((size_t)S.nPoses * 8, 256);
+  const int ctas = std::min(N, m->numCtas);
+  if (!d_workspace || workspaceBytes < C.slotBytes * ctas + 256) return fail(SLAM_E_BADARG, "slam_correlate: workspace too small");
+  C.scratch = (unsigned char*)align_up((size_t)d_workspace, 256);
+  C.Kpad = S.Kpad;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 16); return (int)o; };
+  C.oDx = take((size_t)m->P.K * 8); C.oDy = take((size_t)m->P.K * 8);
+  C.oLists = take((size_t)S.nTheta * S.Kpad * 4); C.oCnt = take((size_t)S.nTheta * 4);
+  C.oLeaf = take((size_t)(S.nLeaves + S.nOps + 1) * 8);
+  int dev = 0, optin = 0;
+  SLAM_CUDA(cudaGetDevice(&dev));
+  if (dev != m->device) return fail(SLAM_E_BADARG, "slam_correlate: the current device is not the one the matcher was created on");
+  SLAM_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (off + 1024 > (size_t)optin) return fail(SLAM_E_UNSUPPORTED, "slam_correlate: lists do not fit shared memory");
+  SLAM_CUDA(cudaFuncSetAttribute(correlate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
+  correlate_kernel<<<ctas, 256, off, (cudaStream_t)stream>>>(C, S);
+  SLAM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int slam_blur_clamp(const double* d_in, int32_t rows, int32_t cols, const double* d_taps, int32_t radius,
+                               double* d_tmp, double* d_out, void* stream) {
+  if (!d_in || !d_taps || !d_tmp || !d_out || rows <= 0 || cols <= 0 || radius < 0)
+    return fail(SLAM_E_BADARG, "slam_blur_clamp: bad argument");
+  const size_t n = (size_t)rows * cols;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  blur_axis_kernel<<<blocks, 256, 0, st>>>(d_in, d_tmp, rows, cols, 0, radius, d_taps);
+  blur_axis_kernel<<<blocks, 256, 0, st>>>(d_tmp, d_out, rows, cols, 1, radius, d_taps);
+  min_kernel<<<1, 1024, 0, st>>>(d_out, n, d_tmp);            // d_tmp[0] := probMin
+  clamp_kernel<<<blocks, 256, 0, st>>>(d_out, n, d_tmp);
   SLAM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -64,7 +64,7 @@ class MatcherEngine:
         self._keep = []
         desc = nat.MatcherDesc()
         desc.windowRadius = self.windowRadius
-        self.stageInfo = []
+        self.stageInfo, self.stageLog, self.stageSigma = [], [], []
         for st, ul, sigma, miss, radius, half in (
                 (desc.coarse, self.coarseStep, coarseSigma, missMatchProbAtCoarse, searchRadius, searchHalfRad),
                 (desc.fine, u, scanSigmaInNumGrid, fineMiss, self.coarseStep, fineHalf)):
@@ -84,6 +84,8 @@ class MatcherEngine:
                 self._keep.append(arr)
                 setattr(st, name, arr.ctypes.data_as(nat.c_double_p))
             self.stageInfo.append(dict(unitLength=ul, nHalf=st.nHalf, thetas=thetas, radius=r))
+            self.stageLog.append(math.log(miss))
+            self.stageSigma.append(sigma)
         # every gather must stay inside the window: |point - pose| < maxRange, offsets <= nHalf cells
         margin = self.windowRadius - geom.lidarMaxRange
         if margin < self.stageInfo[0]["nHalf"] * self.coarseStep or margin < self.stageInfo[1]["nHalf"] * u:

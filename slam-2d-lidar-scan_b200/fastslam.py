@@ -95,6 +95,29 @@ class Particle:
             return None
         return float(self._pf.prevHeading[self._i].item())
 
+    # -- the reference's scalar helpers (FastSlam.py:77-120, 137-140), on this particle's state (host arithmetic: the
+    #    batched kernels slam_propose_poses / slam_finish_step do the same for all particles inside update())
+    def updateEstimatedPose(self, currentRawReading):
+        from .matcher import updateEstimatedPose
+        prevRaw = self.prevRawReading
+        est, dist, theta, rawTheta = updateEstimatedPose(currentRawReading, self.prevMatchedReading, prevRaw,
+                                                         self._pf._prevRawHeading[self._i], self.prevMatchedMovingTheta)
+        self._pf._prevRawHeading[self._i] = rawTheta                                        # :102-105
+        return est, dist, theta
+
+    def getMovingTheta(self, matchedReading):
+        x, y = self.xTrajectory, self.yTrajectory
+        from .matcher import getMovingTheta
+        return getMovingTheta(matchedReading, x, y)
+
+    def updateTrajectory(self, matchedReading):
+        pf, i = self._pf, self._i
+        row = torch.zeros((pf.numParticles, 2), dtype=torch.float64, device=pf.geom.device)
+        if pf._traj:
+            row.copy_(pf._traj[-1])
+        row[i, 0], row[i, 1] = matchedReading['x'], matchedReading['y']
+        pf._traj.append(row)
+
     def update(self, reading, count):
         """Particle.update (FastSlam.py:122-135) for this particle only."""
         self._pf._update(self._i, self._i + 1, reading, count)

@@ -261,3 +261,99 @@ def test_sharding_is_invisible_across_two_gpus():
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
                         os.path.join(root, "tools", "check_sharded.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "SHARDED_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def _oracle_stage(ref, mp, x, y, th, rng, ul, sigma, miss, searchRadius, estDist, estTheta, fine, matchMax, prob=None):
+    """One stage of the oracle, piece by piece -> (xr0, yr0, probSP, convTotal, (it, iy, ix), conf)."""
+    g = ref.geom
+    R = 1.1 * g.maxRange + mp[0]
+    bx, by, space = O.occupancy_scatter(g, ref.occupancyGridVisited, ref.occupancyGridTotal, x, y, ul, R, miss)
+    if prob is None:
+        prob = O.likelihood_field(space, sigma)
+    px, py = O.beam_endpoints(g, x, y, th, rng)
+    axis = O.offset_axis(searchRadius, ul)
+    if fine:
+        rv = tw = np.zeros((axis.shape[0], axis.shape[0]))
+    else:
+        rv, tw = O.motion_priors(axis, ul, estDist, estTheta, mp[3], mp[4], mp[5])
+    thetas = O.theta_offsets(g, mp[1])
+    with np.errstate(invalid="ignore"):
+        vol = O.correlation_volume(prob, px, py, x, y, bx, by, ul, thetas, axis, rv, tw)
+        idx, conf = O.choose_pose(vol, matchMax)
+    pose = (x + axis[idx[2]] * ul, y + axis[idx[1]] * ul, th + thetas[idx[0]])
+    return bx, by, prob, vol, pose, conf
+
+
+@pytest.mark.gpu
+def test_stage_methods_match_the_oracle_stage_by_stage(S, frames):
+    """The reference's public stage API (ScanMatcher_OGBased.py:20-45, 81-176): frameSearchSpace ->
+    searchToMatch (coarse, argmax and sampled, with and without heading prior) -> frameSearchSpace -> searchToMatch
+    (fine), each through the stage-level C entries, against the oracle's stages on the same map: probSP and convTotal
+    bit for bit, same pose, same position in numpy's RNG stream."""
+    from scipy.ndimage import gaussian_filter
+    init = {"x": frames[0]["x"], "y": frames[0]["y"]}
+    ogp = (30, 30, init, 0.1, np.pi, 180, 10, 0.5)
+    smp = (1.0, 0.3, 2, 0.1, 0.25, 0.3, 0.15, 2)
+    og, ref = S.OccupancyGrid(*ogp), O.OccupancyGrid(*ogp)
+    sm = S.ScanMatcher(og, *smp)
+    for fr in frames[:4]:
+        og.updateOccupancyGrid(reading(fr)); ref.updateOccupancyGrid(reading(fr))
+    fr = reading(frames[4])
+    x, y, th, rng = fr["x"], fr["y"], fr["theta"], np.asarray(fr["range"], dtype=np.float64)
+    cstep, csig = smp[7] * og.unitGridSize, smp[2] / smp[7]
+    xr, yr, prob = sm.frameSearchSpace(x, y, cstep, csig, smp[6])
+    bx, by, prob2, _, _, _ = _oracle_stage(ref, smp, x, y, th, rng, cstep, csig, smp[6], smp[0], 0.12, None, False, True)
+    assert xr[0] == bx and yr[0] == by and np.array_equal(prob, prob2)
+    pose = None
+    for matchMax, mt in ((True, None), (False, 0.4), (False, None)):
+        np.random.seed(11)
+        got = sm.searchToMatch(prob, x, y, th, rng, xr, yr, smp[0], smp[1], cstep, 0.12, mt, fineSearch=False, matchMax=matchMax)
+        after = np.random.random_sample()
+        np.random.seed(11)
+        _, _, _, vol, pose, conf = _oracle_stage(ref, smp, x, y, th, rng, cstep, csig, smp[6], smp[0], 0.12, mt, False, matchMax)
+        assert after == np.random.random_sample()                               # same number of draws consumed
+        assert np.array_equal(got[3], vol)                                       # convTotal
+        assert (got[2]["x"], got[2]["y"], got[2]["theta"]) == pose
+        assert got[4] == pytest.approx(conf, rel=CONF_RTOL)
+        assert len(got[0]) == len(got[1]) == int((rng < 10).sum())
+    fmiss = smp[6] ** (2 / smp[7])
+    xr, yr, prob = sm.frameSearchSpace(pose[0], pose[1], og.unitGridSize, smp[2], fmiss)
+    _, _, prob2, vol, fpose, _ = _oracle_stage(ref, smp, pose[0], pose[1], pose[2], rng, og.unitGridSize, smp[2], fmiss, cstep,
+                                               0.12, None, True, True)
+    assert np.array_equal(prob, prob2)
+    got = sm.searchToMatch(prob, pose[0], pose[1], pose[2], rng, xr, yr, cstep, smp[1], og.unitGridSize, 0.12, None, fineSearch=True)
+    assert np.array_equal(got[3], vol) and (got[2]["x"], got[2]["y"], got[2]["theta"]) == fpose
+    # generateProbSearchSpace on an arbitrary array == scipy + min + clamp; helpers == the reference expressions
+    a = np.random.default_rng(2).normal(-1.0, 0.7, (57, 83))
+    want = gaussian_filter(a, sigma=1.3)
+    want[want > 0.5 * want.min()] = 0
+    assert np.array_equal(sm.generateProbSearchSpace(a, 1.3), want)
+    px, py = sm.covertMeasureToXY(x, y, th, rng)
+    px2, py2 = O.beam_endpoints(ref.geom, x, y, th, rng)
+    assert np.array_equal(px, px2) and np.array_equal(py, py2)
+    qx, qy = sm.rotate((x, y), (px, py), 0.1)
+    assert np.array_equal(qx, x + np.cos(0.1) * (px - x) - np.sin(0.1) * (py - y))
+    xi, yi = sm.convertXYToSearchSpaceIdx(px, py, xr[0], yr[0], 0.1)
+    assert np.array_equal(xi, ((px - xr[0]) / 0.1).astype(int)) and np.array_equal(yi, ((py - yr[0]) / 0.1).astype(int))
+
+
+@pytest.mark.gpu
+def test_nan_score_volume_argmax_returns_numpys_first_nan(S, frames):
+    """numpy's argmax returns the first NaN; np.random.choice raises on NaN probabilities (:134-138)."""
+    init = {"x": frames[0]["x"], "y": frames[0]["y"]}
+    ogp = (30, 30, init, 0.1, np.pi, 180, 10, 0.5)
+    smp = (1.0, 0.3, 2, 0.1, 0.25, 0.3, 0.15, 2)
+    og, ref = S.OccupancyGrid(*ogp), O.OccupancyGrid(*ogp)
+    sm = S.ScanMatcher(og, *smp)
+    fr = reading(frames[1])
+    x, y, th, rng = fr["x"], fr["y"], fr["theta"], np.asarray(fr["range"], dtype=np.float64)
+    cstep, csig = smp[7] * og.unitGridSize, smp[2] / smp[7]
+    xr, yr, prob = sm.frameSearchSpace(x, y, cstep, csig, smp[6])
+    prob = prob.copy()
+    prob[prob.shape[0] // 2 - 3: prob.shape[0] // 2 + 3, :] = np.nan
+    _, _, _, vol, pose, _ = _oracle_stage(ref, smp, x, y, th, rng, cstep, csig, smp[6], smp[0], 0.1, None, False, True, prob=prob)
+    got = sm.searchToMatch(prob, x, y, th, rng, xr, yr, smp[0], smp[1], cstep, 0.1, None, fineSearch=False, matchMax=True)
+    assert np.isnan(vol).any() and np.array_equal(np.isnan(got[3]), np.isnan(vol))
+    assert (got[2]["x"], got[2]["y"], got[2]["theta"]) == pose
+    with pytest.raises(ValueError):
+        sm.searchToMatch(prob, x, y, th, rng, xr, yr, smp[0], smp[1], cstep, 0.1, None, fineSearch=False, matchMax=False)
