@@ -9,6 +9,10 @@
 * ``fastslam``   Algorithm/FastSlam.py:152-162 (best particle = max weight, :165-170)
 * ``mapping``    Utils/OccupancyGrid.py:198-200 (known poses)
 
+``--gt <corrected log>`` additionally scores the trajectory against ground truth (evaluate.py: ATE / RPE; the
+reference's own compareGT, ScanMatcher_OGBased.py:270-289, is only a per-step debugging printout) and writes
+``<out>_accuracy.json`` with the raw odometry's scores next to it.
+
 Maps are pre-sized (``--map`` metres, centred on the first pose) because this implementation does not expand them;
 the reference's defaults otherwise (unit 0.02 m, 180 beams over pi, 10 m range -- :292-294 / FastSlam.py:197-199).
 Outputs ``<out>_trajectory.npy`` ([T][3] matched poses, best particle for fastslam) and ``<out>_map.npz``
@@ -19,6 +23,7 @@ import time
 
 import numpy as np
 
+from .evaluate import evaluate_trajectory
 from .fastslam import ParticleFilter
 from .grid import OccupancyGrid
 from .matcher import ScanMatcher, getMovingTheta, readJson, updateEstimatedPose, updateTrajectory
@@ -84,6 +89,7 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--frames", type=int, default=None)
     ap.add_argument("--device", default=None)
+    ap.add_argument("--gt", default=None, help="ground-truth JSON of the same stamps (e.g. intel_corrected_log)")
     a = ap.parse_args(argv)
     data = readJson(a.data)
     first = data[sorted(data.keys())[0]]
@@ -112,6 +118,18 @@ def main(argv=None):
     np.savez_compressed(a.out + "_map.npz", visited=og.occupancyGridVisited.astype(np.float32),
                         total=og.occupancyGridTotal.astype(np.float32), mapXLim=og.mapXLim, mapYLim=og.mapYLim)
     log("%d frames -> %s_trajectory.npy, %s_map.npz" % (len(traj), a.out, a.out))
+    if a.gt:
+        import json
+        gt = readJson(a.gt)
+        keys = sorted(data.keys())[:len(traj)]
+        truth = np.array([[gt[k]['x'], gt[k]['y'], gt[k]['theta']] for k in keys])
+        raw = np.array([[data[k]['x'], data[k]['y'], data[k]['theta']] for k in keys])
+        acc = dict(mode=a.mode, particles=a.particles if a.mode == "fastslam" else 1, unit=unit,
+                   estimate=evaluate_trajectory(traj, truth), raw_odometry=evaluate_trajectory(raw, truth))
+        json.dump(acc, open(a.out + "_accuracy.json", "w"), indent=1)
+        log("ATE rmse %.3f m (raw odometry %.3f m), RPE %.4f m / %.4f rad per step" % (
+            acc["estimate"]["ate"]["rmse"], acc["raw_odometry"]["ate"]["rmse"], acc["estimate"]["rpe"]["trans_rmse"],
+            acc["estimate"]["rpe"]["rot_rmse"]))
 
 
 if __name__ == "__main__":
