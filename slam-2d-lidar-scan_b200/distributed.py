@@ -50,6 +50,7 @@ class ShardedParticleFilter:
         self.numParticles = numParticles
         self.lo, self.hi = shard_bounds(numParticles, self.world)[self.rank]
         self.local = ParticleFilter(self.hi - self.lo, ogParameters, smParameters, device=device)
+        self.local._tightenBound = False     # every rank must grow its maps in the same step (bound from the readings only)
         dev = self.local.geom.device
         nL = self.hi - self.lo
         # all-gather payload per rank: nL rows (unnormalised weight, x, y, theta) + one row carrying the OR of the
@@ -96,7 +97,7 @@ class ShardedParticleFilter:
         self.local.d2hBytes += 24
         if self.local.ignoreMissingHeading:
             bits &= ~nat.ST_HEADING_MISSING
-        raise_for_status(bits)
+        raise_for_status(bits & ~self.local.ignoreStatusBits)
         self.lastVariance = var
         return fired
 

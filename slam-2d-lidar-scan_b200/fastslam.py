@@ -147,6 +147,11 @@ class ParticleFilter:
         self._slots_h = np.arange(n, dtype=np.int32)
         self.slots = torch.arange(n, dtype=torch.int32, device=dev)
         self.resampleCopies = 0              # lattices physically copied by resample() so far
+        # map expansion (OccupancyGrid.py:108-125): conservative host-side box around all particle poses, so that the
+        # lattices can be grown BEFORE a launch would leave them, without a device read-back per step
+        self._bound = None
+        self._tightenBound = True            # read the true pose extremes back (one sync) before actually growing
+        self.expansions = 0
         self.prevMatched = torch.zeros((n, 3), **f64)
         self.prevHeading = torch.zeros(n, **f64)
         self.hasHeading = torch.zeros(n, **i32)
@@ -178,6 +183,8 @@ class ParticleFilter:
         # The reference dies with a TypeError (None + float, FastSlam.py:96) when a particle did not move in the step
         # before a > 0.3 m odometry step; True = carry on with a zero heading prior for that particle instead.
         self.ignoreMissingHeading = False
+        self.ignoreStatusBits = 0            # further status bits not to raise on (e.g. lost particles leaving a fixed-size map)
+        self.expandMaps = True               # grow the maps like the reference (False: fixed size, leaving it is an error)
         self.h2dBytes = 0
         self.d2hBytes = 0
         self._prevRaw = [None] * n
@@ -214,7 +221,7 @@ class ParticleFilter:
         self.d2hBytes += 24
         if self.ignoreMissingHeading:
             bits &= ~nat.ST_HEADING_MISSING
-        raise_for_status(bits)
+        raise_for_status(bits & ~self.ignoreStatusBits)
         self.lastVariance = var
         return fired
 
@@ -342,8 +349,57 @@ class ParticleFilter:
             update_grids(self.geom, self.grids, n, d_stage[:K], matched, status, slots=self.slots[lo:hi])    # :133
         self.kernelLaunches += 3 + (0 if count == 1 else 3 + (1 if rec["mode"] == 1 else 0))
 
+    def _grow(self):
+        """All lattices double around the map centre (geometry.grown): the filter's maps become the lattices a filter
+        pre-sized to that length has.  The matcher is re-planned for the new lattice; particle views are rebuilt."""
+        new, off = self.geom.grown()
+        self.grids = self.geom.rehome(self.grids, new, off)
+        self.geom = new
+        self.engine = MatcherEngine(new, *self.smParameters)
+        self.ogParameters[0], self.ogParameters[1] = new.args[0], new.args[1]
+        self._particles = None
+        self.expansions += 1
+
+    def _ensure_room(self, reading, count):
+        """Grow the maps if this step's search windows (est +- windowRadius, and the fine window around any coarse
+        result) or scan updates could leave them."""
+        if not self.expandMaps:
+            return
+        eng, g = self.engine, self.geom
+        step = eng.searchRadius + eng.coarseStep             # a matched pose is at most this far from its proposal
+        if count == 1 or self._bound is None:
+            if count == 1:
+                b = [reading['x'], reading['x'], reading['y'], reading['y']]      # matched = reading (:123-125)
+            else:
+                b = self._pose_extremes()
+                b = [b[0] - step, b[1] + step, b[2] - step, b[3] + step]
+        else:
+            b = [self._bound[0] - step, self._bound[1] + step, self._bound[2] - step, self._bound[3] + step]
+        # needed: every coarse window est +- windowRadius (:21-27) and every fine window, centred at most searchRadius
+        # further out (:70).  b bounds the poses AFTER this step (proposals +- step), so b +- windowRadius holds both.
+        m = 1.1 * g.lidarMaxRange + eng.searchRadius
+        inside = lambda bb: self.geom.contains(bb[0] - m, bb[1] + m, bb[2] - m, bb[3] + m)
+        if not inside(b) and count > 1 and self._tightenBound:
+            # the running box is conservative: read the true extremes of the proposals back (one sync) before growing --
+            # a map that is large enough must never be touched (growing changes the lattice's coordinate rounding)
+            t = self._pose_extremes()
+            sr = eng.searchRadius
+            if inside([t[0] - sr, t[1] + sr, t[2] - sr, t[3] + sr]):
+                b = [t[0] - step, t[1] + step, t[2] - step, t[3] + step]
+                self._bound = b
+                return
+            b = [t[0] - step, t[1] + step, t[2] - step, t[3] + step]
+        while not inside(b):
+            self._grow()
+        self._bound = b
+
+    def _pose_extremes(self):
+        lo, hi = self.prevMatched[:, :2].min(0).values.cpu().tolist(), self.prevMatched[:, :2].max(0).values.cpu().tolist()
+        return [lo[0], hi[0], lo[1], hi[1]]
+
     def _update(self, lo, hi, reading, count, uniforms=None):
         """Particle.update (FastSlam.py:122-135) for particles [lo, hi): host prep, one H2D copy, launches."""
+        self._ensure_room(reading, count)
         n, dev, N = hi - lo, self.geom.device, self.numParticles
         if self._stage_busy:
             self._stage_ev.synchronize()         # previous async H2D out of the pinned staging buffer has landed

@@ -18,9 +18,11 @@ def require_cuda(device=None):
 
 class LidarGeometry:
     def __init__(self, mapXLength, mapYLength, initXY, unitGridSize, lidarFOV, numSamplesPerRev, lidarMaxRange,
-                 wallThickness, device=None):
+                 wallThickness, device=None, _cells=None):
         xNum = int(mapXLength / unitGridSize)
         yNum = int(mapYLength / unitGridSize)
+        if _cells is not None:          # grown(): the cell count is given exactly (no float division)
+            xNum = yNum = int(_cells)
         if xNum != yNum:
             # the reference mixes xNum / yNum (OccupancyGrid.py:11,13); only square maps are well defined
             raise NotImplementedError("only square maps are supported (mapXLength == mapYLength)")
@@ -28,6 +30,8 @@ class LidarGeometry:
             raise NotImplementedError("at most %d beams per scan" % nat.MAX_BEAMS)
         self.args = (mapXLength, mapYLength, dict(initXY), unitGridSize, lidarFOV, numSamplesPerRev, lidarMaxRange,
                      wallThickness)
+        self.initXY = dict(initXY)
+        self.cells = xNum
         self.unitGridSize = unitGridSize
         self.lidarFOV = lidarFOV
         self.lidarMaxRange = lidarMaxRange
@@ -82,6 +86,26 @@ class LidarGeometry:
         self.localAxis = axis
         self.sector = sec.astype(np.int32)
         self.radius = np.sqrt(xg ** 2 + yg ** 2)
+
+    def grown(self):
+        """The lattice of a map twice as long around the same centre: exactly the lattice a map pre-sized to that
+        length would have (same linspace expression), so an expanded map IS a pre-sized one.  -> (geometry, offset)
+        where old cell (i, j) is new cell (i + offset, j + offset).  Map expansion, OccupancyGrid.py:59-125."""
+        if self.cells % 2:
+            raise NotImplementedError("map expansion needs an even number of cells per side")
+        new = LidarGeometry(2 * self.args[0], 2 * self.args[1], self.initXY, self.unitGridSize, self.lidarFOV,
+                            self.numSamplesPerRev, self.lidarMaxRange, self.wallThickness, device=self.device,
+                            _cells=2 * self.cells)
+        return new, self.cells // 2
+
+    def rehome(self, grids, new, offset):
+        """Counts of lattices ``grids`` [n][G][pitch][2] copied into fresh lattices of geometry ``new`` (device copy)."""
+        out = new.new_grids(grids.shape[0])
+        out[:, offset:offset + self.G, offset:offset + self.G, :] = grids[:, :, :self.G, :]
+        return out
+
+    def contains(self, x0, x1, y0, y1):
+        return x0 >= self.mapXLim[0] and x1 <= self.mapXLim[1] and y0 >= self.mapYLim[0] and y1 <= self.mapYLim[1]
 
     def update_workspace(self, n):
         """Device scratch of slam_update_grid for n particles, one buffer per CUDA stream (grown on demand)."""

@@ -8,6 +8,16 @@ from .engine import raise_for_status, update_grids
 from .geometry import LidarGeometry
 
 
+def scan_reach(ranges, maxRange, wallThickness):
+    """Largest distance from the pose at which this scan can touch a cell (OccupancyGrid.py:138-143): a beam empties
+    r < range - wall/2 (only if range < maxRange) and marks range - wall/2 < r < range + wall/2; the lidar-local patch
+    ends at sqrt(2) * maxRange, so longer beams (the logs' 81.83 m sentinel) touch nothing."""
+    r = np.asarray(ranges, dtype=np.float64)
+    hit = r[r - wallThickness / 2 < 1.4143 * maxRange]
+    reach = float(hit.max() + wallThickness / 2) if hit.size else 0.0
+    return min(reach, 1.4143 * maxRange)
+
+
 class OccupancyGrid:
     def __init__(self, mapXLength, mapYLength, initXY, unitGridSize, lidarFOV, numSamplesPerRev, lidarMaxRange,
                  wallThickness, *, device=None, _geometry=None, _grids=None, _slot=0, _slotmap=None):
@@ -74,18 +84,60 @@ class OccupancyGrid:
         return -1
 
     def checkAndExapndOG(self, x, y):
-        """The reference grows the map here (OccupancyGrid.py:120-125); this implementation works on pre-sized
-        lattices (SURVEY.md A.8 lists the reference's expansion defects), so leaving the map is an error."""
-        if self.checkMapToExpand(x, y) != -1:
-            raise IndexError("coordinates outside the pre-sized map; construct the OccupancyGrid large enough")
+        """Grow the map until it holds the points (OccupancyGrid.py:120-125).  Deviation from the reference, whose
+        expansion has defects (non-uniform inserted coordinates, stale indices): the map doubles around
+        its centre and becomes exactly the lattice a map pre-sized to that length has ("virtually pre-sized")."""
+        while self.checkMapToExpand(x, y) != -1:
+            self.expandOccupancyGrid(self.checkMapToExpand(x, y))
 
     def expandOccupancyGrid(self, expandDirection):
-        raise NotImplementedError("map expansion is out of scope (pre-size the map)")
+        """OccupancyGrid.py:93-101.  Every direction grows the map symmetrically (see checkAndExapndOG)."""
+        if self._slotmap is not None:
+            raise IndexError("a particle's map grows with its filter (ParticleFilter expands all lattices together)")
+        new, off = self.geom.grown()
+        self._grids = self.geom.rehome(self._grids, new, off)
+        self._adopt(new)
+
+    def _adopt(self, geom):
+        self.geom = geom
+        self.mapXLim = list(geom.mapXLim)
+        self.mapYLim = list(geom.mapYLim)
+
+    def _touched_extent(self, reading, dTheta=0):
+        """World bounding box of the cells this scan empties or marks (OccupancyGrid.py:131-145), or None."""
+        g = self.geom
+        ranges = np.asarray(reading['range'], dtype=np.float64)
+        off = int(np.rint((reading['theta'] + dTheta) / (2 * np.pi) * g.numSpokes))              # :131
+        beam = (g.sector - (g.spokesStartIdx + off)) % g.numSpokes                              # inverse of :134
+        valid = beam < g.numSamplesPerRev
+        b = np.where(valid, beam, 0)
+        lo, hi = (ranges - g.wallThickness / 2)[b], (ranges + g.wallThickness / 2)[b]
+        touched = valid & (((ranges[b] < g.lidarMaxRange) & (g.radius < lo)) | ((g.radius > lo) & (g.radius < hi)))
+        ys, xs = np.nonzero(touched)
+        if ys.size == 0:
+            return None
+        ax = g.localAxis
+        return (reading['x'] + ax[xs.min()], reading['x'] + ax[xs.max()], reading['y'] + ax[ys.min()],
+                reading['y'] + ax[ys.max()])
+
+    def _cover(self, x0, x1, y0, y1):
+        """Expand (standalone maps only) until the box lies inside the map."""
+        if not self.geom.contains(x0, x1, y0, y1):
+            self.checkAndExapndOG(np.array([x0, x1]), np.array([y0, y1]))
 
     def updateOccupancyGrid(self, reading, dTheta=0, update=True):
         """OccupancyGrid.py:127-152 on the GPU (slam_update_grid)."""
         if not update:
             raise NotImplementedError("update=False (coordinate lists) has no caller in the reference")
+        if self._slotmap is None:
+            m = scan_reach(reading['range'], self.lidarMaxRange, self.wallThickness) + self.unitGridSize
+            x, y = reading['x'], reading['y']
+            if not self.geom.contains(x - m, x + m, y - m, y + m):
+                # close to the border: decide with the cells the scan really touches (a map that is large enough is
+                # never grown -- growing changes the lattice's coordinate rounding)
+                box = self._touched_extent(reading, dTheta)
+                if box is not None:
+                    self._cover(*box)
         pose = torch.tensor([reading['x'], reading['y'], reading['theta'] + dTheta], dtype=torch.float64)
         rng = torch.as_tensor(np.asarray(reading['range'], dtype=np.float64))
         self._pose.copy_(pose)

@@ -22,11 +22,11 @@ class ScanMatcher:
         self.turnSigma = turnSigma
         self.missMatchProbAtCoarse = missMatchProbAtCoarse
         self.maxMoveDeviation = maxMoveDeviation
-        self.engine = _engine or MatcherEngine(og.geom, searchRadius, searchHalfRad, scanSigmaInNumGrid, moveRSigma,
-                                               maxMoveDeviation, turnSigma, missMatchProbAtCoarse, coarseFactor,
-                                               fineSearchHalfRad=fineSearchHalfRad)
+        self._fineSearchHalfRad = fineSearchHalfRad
+        self._shared = _engine is not None          # a particle's matcher uses its filter's engine
+        self._engine = _engine or self._plan(og.geom)
         dev = og.geom.device
-        n2 = self.engine.nOffC ** 2
+        n2 = self._engine.nOffC ** 2
         f64 = dict(dtype=torch.float64, device=dev)
         self._ranges = torch.zeros(og.geom.numSamplesPerRev, **f64)
         self._est = torch.zeros(3, **f64)
@@ -40,10 +40,30 @@ class ScanMatcher:
         self.debug = False          # True: keep probSP / convTotal of the last call in self.last
         self.last = None
 
+    def _plan(self, geom):
+        return MatcherEngine(geom, self.searchRadius, self.searchHalfRad, self.scanSigmaInNumGrid, self.moveRSigma,
+                             self.maxMoveDeviation, self.turnSigma, self.missMatchProbAtCoarse, self.coarseFactor,
+                             fineSearchHalfRad=self._fineSearchHalfRad)
+
+    @property
+    def engine(self):
+        """Device plan for the map's CURRENT lattice (re-planned after the map has grown)."""
+        if not self._shared and self._engine.geom is not self.og.geom:
+            self._engine = self._plan(self.og.geom)
+        return self._engine
+
+    def _cover_search(self, x, y):
+        """frameSearchSpace grows the map until it holds the search window est +- (1.1 maxRange + searchRadius)
+        (:21-27): the same test, before the fused launch (a map that is large enough is never touched)."""
+        if not self._shared:
+            m = 1.1 * self.og.lidarMaxRange + self.searchRadius
+            self.og._cover(x - m, x + m, y - m, y + m)
+
     def matchScan(self, reading, estMovingDist, estMovingTheta, count, matchMax=True):
         """Coarse-to-fine correlative match (ScanMatcher_OGBased.py:47-79) -> (matchedReading, coarseConfidence)."""
         if count == 1:
             return reading, 1
+        self._cover_search(reading['x'], reading['y'])
         eng = self.engine
         rng = np.asarray(reading['range'], dtype=np.float64)
         self._ranges.copy_(torch.from_numpy(rng))
@@ -58,15 +78,24 @@ class ScanMatcher:
             # np.random.choice(arange(n), 1, p=...) draws exactly one double from the legacy global RandomState
             self._u.copy_(torch.from_numpy(np.random.random_sample(1)))
             u = self._u
-        self._status.zero_()        # the kernels OR their bits in; this standalone matcher reports per call
-        dbg = bufs = None
-        if self.debug:
-            dbg, bufs = eng.debug_buffers(1)
-        eng.match(self.og.device_grid, 1, self._ranges, self._est, self._rv, tw, u, self._outPose, self._outConf,
-                  self._outIdx, self._status, debug=dbg)
-        pose = self._outPose.cpu().numpy()
-        conf = float(self._outConf.item())
-        raise_for_status(int(self._status.item()))
+        while True:
+            self._status.zero_()        # the kernels OR their bits in; this standalone matcher reports per call
+            dbg = bufs = None
+            if self.debug:
+                dbg, bufs = eng.debug_buffers(1)
+            eng.match(self.og.device_grid, 1, self._ranges, self._est, self._rv, tw, u, self._outPose, self._outConf,
+                      self._outIdx, self._status, debug=dbg)
+            pose = self._outPose.cpu().numpy()
+            conf = float(self._outConf.item())
+            bits = int(self._status.item())
+            if (bits & nat.ST_WINDOW_OUTSIDE_MAP) and not self._shared:
+                # the FINE window (around the coarse result) left the map: the reference grows the map in its second
+                # frameSearchSpace call (:70); here the map grows and the fused match is repeated on the new lattice
+                self.og.expandOccupancyGrid(0)
+                eng = self.engine
+                continue
+            break
+        raise_for_status(bits)
         idx = self._outIdx.cpu().numpy()
         self.lastIdx = (tuple(int(v) for v in idx[:3]), tuple(int(v) for v in idx[3:]))
         if bufs is not None:

@@ -254,13 +254,28 @@ def test_exact_cdf_walk_equals_certified_parallel_inversion(S, frames):
     assert len(np.unique(out[0][0][:, 2])) > 1          # particles really diverged through sampling
 
 
-def test_window_outside_map_raises_like_an_unexpandable_map(S, frames):
+def test_window_outside_map_grows_the_map_or_raises_when_fixed(S, frames):
+    """A 20 m map cannot hold the +-12 m search window: the standalone classes grow it like the reference
+    (ScanMatcher_OGBased.py:27); a filter told to keep its maps fixed reports the window like numpy would
+    (IndexError)."""
     init = {"x": frames[0]["x"], "y": frames[0]["y"]}
     og = S.OccupancyGrid(20, 20, init, 0.1, np.pi, 180, 10, 0.5)
     sm = S.ScanMatcher(og, 1.0, 0.3, 2, 0.1, 0.25, 0.3, 0.15, 2)
     og.updateOccupancyGrid(reading(frames[0]))
+    matched, conf = sm.matchScan(reading(frames[1]), 0.0, None, 2)
+    assert og.geom.args[0] == 40 and og.mapXLim[1] - og.mapXLim[0] == pytest.approx(40.0)
+    big = S.OccupancyGrid(40, 40, init, 0.1, np.pi, 180, 10, 0.5)
+    smBig = S.ScanMatcher(big, 1.0, 0.3, 2, 0.1, 0.25, 0.3, 0.15, 2)
+    big.updateOccupancyGrid(reading(frames[0]))
+    m2, c2 = smBig.matchScan(reading(frames[1]), 0.0, None, 2)
+    assert (matched["x"], matched["y"], matched["theta"], conf) == (m2["x"], m2["y"], m2["theta"], c2)
+    pf = S.ParticleFilter(2, [20, 20, init, 0.1, np.pi, 10, 180, 0.5], [1.0, 0.3, 2, 0.1, 0.25, 0.3, 0.15, 2])
+    pf.expandMaps = False
+    pf.updateParticles(reading(frames[0]), 1)
+    pf.weightUnbalanced()
+    pf.updateParticles(reading(frames[1]), 2)
     with pytest.raises(IndexError):
-        sm.matchScan(reading(frames[1]), 0.0, None, 2)
+        pf.weightUnbalanced()
 
 
 def test_360_beam_full_circle_scan_matches_oracle(S):

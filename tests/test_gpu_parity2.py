@@ -357,3 +357,51 @@ def test_nan_score_volume_argmax_returns_numpys_first_nan(S, frames):
     assert (got[2]["x"], got[2]["y"], got[2]["theta"]) == pose
     with pytest.raises(ValueError):
         sm.searchToMatch(prob, x, y, th, rng, xr, yr, smp[0], smp[1], cstep, 0.1, None, fineSearch=False, matchMax=False)
+
+
+@pytest.mark.gpu
+def test_map_expansion_equals_the_presized_lattice(S, frames):
+    """F1 (OccupancyGrid.py:59-125): a map that starts at the reference's default 10 m grows (doubling around its
+    centre) into exactly the lattice of a map pre-sized to the final length, so the driver loop gives the same poses
+    and the same counts as on the pre-sized map -- for the standalone classes and for a particle filter."""
+    from slam_2d_lidar_scan_b200.drivers import run_scanmatch
+    init = {"x": frames[0]["x"], "y": frames[0]["y"]}
+    smp = (1.4, 0.25, 2, 0.1, 0.25, 0.3, 0.15, 5)
+    data = {"%03d" % i: reading(fr) for i, fr in enumerate(frames[:8])}
+
+    def run(length):
+        og = S.OccupancyGrid(length, length, init, 0.05, np.pi, 180, 10, 0.25)
+        sm = S.ScanMatcher(og, *smp)
+        poses, confs = run_scanmatch(data, og, sm)
+        return og, poses, confs
+    small, p1, c1 = run(10)
+    big, p2, c2 = run(small.geom.args[0])
+    assert small.geom.args[0] >= 40 and small.geom.G == big.geom.G and small.mapXLim == big.mapXLim
+    assert np.array_equal(small.geom.gridX, big.geom.gridX)
+    assert np.array_equal(p1, p2) and np.array_equal(c1, c2)
+    assert np.array_equal(small.occupancyGridVisited, big.occupancyGridVisited)
+    assert np.array_equal(small.occupancyGridTotal, big.occupancyGridTotal)
+    # counts written before an expansion are re-homed exactly
+    og = S.OccupancyGrid(30, 30, init, 0.1, np.pi, 180, 10, 0.5)
+    og.updateOccupancyGrid(reading(frames[0]))
+    before, lim = og.occupancyGridTotal, list(og.mapXLim)
+    og.checkAndExapndOG(np.array([init["x"] + 20.0]), np.array([init["y"]]))
+    off = (og.geom.G - before.shape[0]) // 2
+    assert og.mapXLim[1] >= init["x"] + 20.0 and og.mapXLim != lim
+    after = og.occupancyGridTotal
+    assert np.array_equal(after[off:off + before.shape[0], off:off + before.shape[1]], before)
+    assert after.sum() - 2.0 * after.size == before.sum() - 2.0 * before.size
+    # particle filter: all lattices grow together
+    def runpf(length):
+        np.random.seed(9)
+        pf = S.ParticleFilter(4, [length, length, init, 0.05, np.pi, 10, 180, 0.25], list(smp))
+        for count, fr in enumerate(frames[:5], start=1):
+            pf.updateParticles(reading(fr), count)
+            pf.weightUnbalanced()
+        return pf
+    a = runpf(10)
+    b = runpf(a.geom.args[0])
+    assert a.expansions >= 2 and b.expansions == 0
+    assert np.array_equal(a.poses(), b.poses()) and torch.equal(a.weights, b.weights)
+    for i in range(4):
+        assert np.array_equal(a.particles[i].og.occupancyGridVisited, b.particles[i].og.occupancyGridVisited)

@@ -22,7 +22,8 @@ from slam_2d_lidar_scan_b200.evaluate import evaluate_trajectory  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--particles", default="10,1024,8192")
-ap.add_argument("--unit", type=float, default=0.05)
+ap.add_argument("--unit", type=float, default=0.1)
+ap.add_argument("--map", type=float, default=100.0, help="fixed map side [m] (no expansion: lost particles are clipped)")
 ap.add_argument("--frames", type=int, default=910)
 ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "r2_accuracy.json"))
 a = ap.parse_args()
@@ -30,12 +31,14 @@ d = np.load(os.path.join(ROOT, "tests", "golden", "intel_full.npz"))
 T = min(a.frames, len(d["poses"]))
 raw, ranges, truth = d["poses"][:T], d["ranges"][:T], d["truth"][:T]
 init = {"x": float(raw[0, 0]), "y": float(raw[0, 1])}
-res = dict(unit=a.unit, frames=T, raw_odometry=evaluate_trajectory(raw, truth), runs=[])
+res = dict(unit=a.unit, map=a.map, frames=T, raw_odometry=evaluate_trajectory(raw, truth), runs=[])
 for n in (int(v) for v in a.particles.split(",")):
     np.random.seed(0)
-    pf = S.ParticleFilter(n, [72, 72, init, a.unit, np.pi, 10, 180, 5 * a.unit], [1.4, 0.25, 2, 0.1, 0.25, 0.3, 0.15, 5])
+    pf = S.ParticleFilter(n, [a.map, a.map, init, a.unit, np.pi, 10, 180, 5 * a.unit], [1.4, 0.25, 2, 0.1, 0.25, 0.3, 0.15, 5])
     pf.keepTrajectory = False
     pf.ignoreMissingHeading = True
+    pf.expandMaps = False                # a particle that leaves the 100 m map is lost anyway; its windows are clipped
+    pf.ignoreStatusBits = 1 | 2 | 8
     hist = torch.zeros((T, n, 3), dtype=torch.float64, device=pf.geom.device)
     torch.cuda.synchronize()
     t0 = time.time()
