@@ -200,6 +200,7 @@ def run_b200(args):
     spf = ShardedParticleFilter(nLocal * world, spec["og"], spec["sm"], device=dev)
     pf = spf.local
     pf.keepTrajectory = False
+    pf.expandMaps = False               # pre-sized 50 m lattices; a window leaving them fails the run
     pf.ignoreMissingHeading = True      # ~1e5 sampled particle-steps: the reference's None + float TypeError (a particle that
                                         # did not move before a > 0.3 m odometry step) does occur; keep going like the kernels do
     geomBytes = pf.grids.numel() * 4
