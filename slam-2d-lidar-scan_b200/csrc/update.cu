@@ -79,7 +79,11 @@ __device__ __forceinline__ int beam_of(int sector, int shift, int numSpokes) {
   return b < 0 ? b + numSpokes : b;              // sector, shift in [0, numSpokes)
 }
 
-// Fast path: thread owns local cells; loops over a chunk of particles with the table entry in registers.
+// Fast path: thread owns a lidar-local cell and loops over a chunk of particles.  All particles share the scan; only
+// the heading (quantised to whole spokes, :131) differs, so a chunk of 32 particles has a handful of DISTINCT sector
+// shifts: the cell's empty / hit flags are evaluated once per distinct shift (2 bits each in a 64-bit mask) and the
+// particle loop only does the read-modify-writes.  Blocks whose cells lie outside the union of the chunk's beam fans
+// or beyond the reach of the scan leave before the interval tables are even built.
 constexpr int UPD_CHUNK = 32;
 __global__ void __launch_bounds__(256) update_fast_kernel(UpdParams P) {
   // per-sector interval tables of this scan: a cell of beam b is seen-empty iff r < loE[b] and hit iff lo[b] < r < hi[b]
@@ -89,8 +93,49 @@ __global__ void __launch_bounds__(256) update_fast_kernel(UpdParams P) {
   double* s_lo = s_tab + P.numSpokes;
   double* s_hi = s_tab + 2 * P.numSpokes;
   __shared__ int4 s_prep[UPD_CHUNK];
+  __shared__ size_t s_lat[UPD_CHUNK];
+  __shared__ int s_fan[2];      // sectors any particle of the chunk can look at: [start, start + length) mod numSpokes
+  __shared__ int s_dshift[UPD_CHUNK], s_didx[UPD_CHUNK], s_nd;     // distinct shifts, particle -> index into them
   const int p0 = blockIdx.y * UPD_CHUNK;
   const int np = min(UPD_CHUNK, P.N - p0);
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x, nS = P.numSpokes;
+    int4 pr = make_int4(0, 0, 0, 0);
+    if (lane < np) {
+      pr = P.prep[p0 + lane];
+      s_prep[lane] = pr;
+      s_lat[lane] = lattice_of(P, p0 + lane);
+    }
+    // union of the particles' beam fans (headings of a chunk differ by a few spokes)
+    const int ref = __shfl_sync(0xffffffffu, pr.z, 0);
+    int d = lane < np ? pr.z - ref : 0;
+    d = ((d + nS / 2) % nS + nS) % nS - nS / 2;        // signed circular distance to the first particle's shift
+    const int dmin = __reduce_min_sync(0xffffffffu, d), dmax = __reduce_max_sync(0xffffffffu, d);
+    if (lane == 0) { s_fan[0] = ((ref + dmin) % nS + nS) % nS; s_fan[1] = P.K + (dmax - dmin); }
+    // distinct shifts: the lowest lane of every group of equal shifts is its leader
+    const unsigned grp = __match_any_sync(0xffffffffu, lane < np ? pr.z : -1 - lane);
+    const bool leader = lane < np && (__ffs(grp) - 1) == lane;
+    const unsigned leaders = __ballot_sync(0xffffffffu, leader);
+    if (leader) s_dshift[__popc(leaders & ((1u << lane) - 1u))] = pr.z;
+    if (lane < np) s_didx[lane] = __popc(leaders & ((1u << (__ffs(grp) - 1)) - 1u));
+    if (lane == 0) s_nd = __popc(leaders);
+  }
+  __syncthreads();
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  int sec = 0;
+  double r = 0.0;
+  bool alive = cell < P.L * P.L;
+  if (alive) {   // cells no particle of the chunk can touch: outside the union of the fans, or beyond the reach of the scan
+    sec = P.sector[cell];
+    int rel = sec - s_fan[0];
+    if (rel < 0) rel += P.numSpokes;
+    alive = rel < s_fan[1];
+    if (alive) {
+      r = P.radius[cell];
+      alive = r < P.reach[0];
+    }
+  }
+  if (!__syncthreads_or(alive)) return;
   for (int k = threadIdx.x; k < P.numSpokes; k += blockDim.x) {
     double loE = -INFINITY, lo = INFINITY, hi = -INFINITY;
     if (k < P.K) {
@@ -101,34 +146,17 @@ __global__ void __launch_bounds__(256) update_fast_kernel(UpdParams P) {
     }
     s_loE[k] = loE; s_lo[k] = lo; s_hi[k] = hi;
   }
-  __shared__ size_t s_lat[UPD_CHUNK];
-  __shared__ int s_fan[2];      // sectors any particle of the chunk can look at: [start, start + length) mod numSpokes
-  if (threadIdx.x < np) {
-    s_prep[threadIdx.x] = P.prep[p0 + threadIdx.x];
-    s_lat[threadIdx.x] = lattice_of(P, p0 + threadIdx.x);
-  }
-  if (threadIdx.x < 32) {       // headings of a chunk differ by a few spokes: union of the particles' beam fans
-    const int nS = P.numSpokes, ref = P.prep[p0].z;
-    int d = 0;
-    if ((int)threadIdx.x < np) {
-      d = P.prep[p0 + threadIdx.x].z - ref;
-      d = ((d + nS / 2) % nS + nS) % nS - nS / 2;      // signed circular distance to the first particle's shift
-    }
-    const int dmin = __reduce_min_sync(0xffffffffu, d), dmax = __reduce_max_sync(0xffffffffu, d);
-    if (threadIdx.x == 0) { s_fan[0] = ((ref + dmin) % nS + nS) % nS; s_fan[1] = P.K + (dmax - dmin); }
-  }
   __syncthreads();
-  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cell >= P.L * P.L) return;
+  if (!alive) return;
   const int ly = cell / P.L, lx = cell - ly * P.L;
-  const int sec = P.sector[cell];
-  {   // cells no particle of the chunk can touch: outside the union of the fans, or beyond the reach of the scan
-    int rel = sec - s_fan[0];
-    if (rel < 0) rel += P.numSpokes;
-    if (rel >= s_fan[1]) return;
+  unsigned long long fm = 0ull;       // 2 bits per distinct shift: bit0 seen empty, bit1 hit
+  const int nd = s_nd;
+  for (int d = 0; d < nd; ++d) {
+    const int beam = beam_of(sec, s_dshift[d], P.numSpokes);
+    const unsigned long long f = (r < s_loE[beam] ? 1ull : 0ull) | ((r > s_lo[beam] && r < s_hi[beam]) ? 2ull : 0ull);
+    fm |= f << (2 * d);
   }
-  const double r = P.radius[cell];
-  if (!(r < P.reach[0])) return;
+  if (fm == 0ull) return;
   const size_t gstride = (size_t)P.G * P.pitch;
   int bad = 0;
   // particles of the chunk in groups of 8: all reads of a group are issued before its writes (distinct particles
@@ -144,16 +172,13 @@ __global__ void __launch_bounds__(256) update_fast_kernel(UpdParams P) {
       const int q = q0 + j;
       if (q < np) {
         const int4 pr = s_prep[q];
-        const int beam = beam_of(sec, pr.z, P.numSpokes);
-        if (pr.w & UPD_PURE) {
-          const unsigned char f = (r < s_loE[beam] ? 1 : 0) | ((r > s_lo[beam] && r < s_hi[beam]) ? 2 : 0);
-          if (f) {
-            const int jx = pr.x + lx, jy = pr.y + ly;
-            if (jx < 0 || jy < 0 || jx >= P.G || jy >= P.G) bad = 1;
-            else {
-              flag[j] = f;
-              ptr[j] = (float2*)P.grid + s_lat[q] * gstride + (size_t)jy * P.pitch + jx;
-            }
+        const unsigned char f = (unsigned char)((fm >> (2 * s_didx[q])) & 3ull);
+        if (f && (pr.w & UPD_PURE)) {
+          const int jx = pr.x + lx, jy = pr.y + ly;
+          if (jx < 0 || jy < 0 || jx >= P.G || jy >= P.G) bad = 1;
+          else {
+            flag[j] = f;
+            ptr[j] = (float2*)P.grid + s_lat[q] * gstride + (size_t)jy * P.pitch + jx;
           }
         }
       }
@@ -171,11 +196,11 @@ __global__ void __launch_bounds__(256) update_fast_kernel(UpdParams P) {
       }
   }
   if (bad) {
-    // conservative: flag every particle of the chunk that was written out of bounds is not tracked per particle
     for (int q = 0; q < np; ++q) {
       const int4 pr = s_prep[q];
       const int jx = pr.x + lx, jy = pr.y + ly;
-      if (jx < 0 || jy < 0 || jx >= P.G || jy >= P.G) atomicOr(&P.status[p0 + q], SLAM_ST_SCAN_OUTSIDE_MAP);
+      if ((pr.w & UPD_PURE) && ((fm >> (2 * s_didx[q])) & 3ull) && (jx < 0 || jy < 0 || jx >= P.G || jy >= P.G))
+        atomicOr(&P.status[p0 + q], SLAM_ST_SCAN_OUTSIDE_MAP);
     }
   }
 }
