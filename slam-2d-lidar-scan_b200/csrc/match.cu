@@ -188,6 +188,7 @@ constexpr int GRP = 2;   // adjacent x offsets handled by one thread (share the 
 
 // Dense field (coarse stage, shared memory): GRP consecutive cells of one row per point.  32-bit shared addressing.
 struct FetchDense {
+  static constexpr bool kWide = false;   // shared-memory gathers: 8 points (16 loads) in flight are enough
   unsigned listS;        // shared address of the sorted unique keys (x << 16 | y)
   unsigned baseS;        // shared address of the field
   unsigned off;          // (dx << 16) + dy, added to the key in one go
@@ -211,6 +212,7 @@ struct FetchDense {
 // (predicated loads) so that the eight gathers of one pairwise step are all in flight together.
 template <bool FAST>
 struct FetchGated {
+  static constexpr bool kWide = true;    // L2-latency gathers: 16 points (32 predicated loads) in flight per thread
   const unsigned* list;
   const unsigned* dil;   // activity bitmap [rows][words], last word of every row always zero
   unsigned listS, dilS;  // shared addresses of the same (FAST plan)
@@ -262,12 +264,13 @@ struct PruneCtx {
   double a1[GRP];      // finished first half of the top-level split
   int h1;              // a1 is valid
   int validMask;       // which of the GRP sums are real hypotheses
+  int pts;             // profiling: points actually gathered (8 per loop trip)
 };
 
 // numpy pairwise_sum for GRP independent sums sharing the index stream: n <= 128 branch inline, recursion
 // (split at n/2 rounded down to a multiple of 8, depth <= 3 for n <= 512) as nested loops around ONE leaf body.
 template <bool PRUNE, class F>
-__device__ __forceinline__ bool leaf_sum_g(const F& f, int off, int n, double (&out)[GRP], const PruneCtx& pc) {
+__device__ __forceinline__ bool leaf_sum_g(const F& f, int off, int n, double (&out)[GRP], PruneCtx& pc) {
   if (n < 8) {
 #pragma unroll
     for (int g = 0; g < GRP; ++g) out[g] = 0.0;
@@ -283,25 +286,51 @@ __device__ __forceinline__ bool leaf_sum_g(const F& f, int off, int n, double (&
 #pragma unroll
   for (int l = 0; l < 8; ++l) f.get(off + l, r[l]);
   const int m = n - (n & 7);
-  for (int i = 8; i < m; i += 8) {
+  int i = 8;
+  auto bound_below_incumbent = [&]() {      // pairwise tree over the CURRENT lane sums: an upper bound of the final score
+    const double inc = lds_f64(pc.bestS);
+    bool all = true;
+#pragma unroll
+    for (int g = 0; g < GRP; ++g) {
+      double x = dadd(dadd(dadd(r[0][g], r[1][g]), dadd(r[2][g], r[3][g])), dadd(dadd(r[4][g], r[5][g]), dadd(r[6][g], r[7][g])));
+      if (pc.h1) x = dadd(pc.a1[g], x);
+      if (((pc.validMask >> g) & 1) && !(x < inc)) all = false;
+    }
+    return all;
+  };
+  if (F::kWide) {
+    for (; i + 16 <= m; i += 16) {
+      double v[16][GRP];
+#pragma unroll
+      for (int l = 0; l < 16; ++l) f.get(off + i + l, v[l]);      // sixteen points in flight; added in numpy's order below
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+#pragma unroll
+        for (int g = 0; g < GRP; ++g) r[l][g] = dadd(r[l][g], v[l][g]);
+      }
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+#pragma unroll
+        for (int g = 0; g < GRP; ++g) r[l][g] = dadd(r[l][g], v[8 + l][g]);
+      }
+      if (PRUNE) {
+        pc.pts += 16;
+        if (bound_below_incumbent()) return true;
+      }
+    }
+  }
+  for (; i < m; i += 8) {
     double v[8][GRP];
 #pragma unroll
     for (int l = 0; l < 8; ++l) f.get(off + i + l, v[l]);       // eight independent gathers in flight
+    if (PRUNE) pc.pts += 8;
 #pragma unroll
     for (int l = 0; l < 8; ++l) {
 #pragma unroll
       for (int g = 0; g < GRP; ++g) r[l][g] = dadd(r[l][g], v[l][g]);
     }
-    if (PRUNE && (i & 8)) {                                       // every 16 points
-      const double inc = lds_f64(pc.bestS);
-      bool all = true;
-#pragma unroll
-      for (int g = 0; g < GRP; ++g) {
-        double x = dadd(dadd(dadd(r[0][g], r[1][g]), dadd(r[2][g], r[3][g])), dadd(dadd(r[4][g], r[5][g]), dadd(r[6][g], r[7][g])));
-        if (pc.h1) x = dadd(pc.a1[g], x);
-        if (((pc.validMask >> g) & 1) && !(x < inc)) all = false;
-      }
-      if (all) return true;
+    if (PRUNE && (F::kWide || (i & 8))) {                         // every 16 points (every 8 in the tail of the wide loop)
+      if (bound_below_incumbent()) return true;
     }
   }
 #pragma unroll
@@ -820,6 +849,10 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
   }
   }
   sc.mark(5);      // D2 (own tiles; the wait for the other warps is accounted to the caller)
+  if (subSlots && !DENSE && lane == 0) {      // profiling: active tiles / cells of the fine field
+    atomicAdd((unsigned long long*)subSlots + 14, (unsigned long long)myCount);
+    if (warp == 0) atomicAdd((unsigned long long*)subSlots + 15, (unsigned long long)nActive);
+  }
   mnOut = mn;
   activeOut = nActive;
   thrOut = anyInactive ? thr : 0.0;     // 0.0 = "not clamped yet"
@@ -836,6 +869,7 @@ struct ScoreArgs {
   int Kpad, Pp, words, nHalf, nOff, nt, t0, nGrpPad;
   unsigned bestS;       // shared address of the branch-and-bound incumbent (fine stage)
   double* bestP;        // the same as a pointer
+  long long* ptsSlot;   // profiling: [0] += points gathered, [1] += points of the evaluated hypotheses without pruning
   BlockScratch* bs;     // per-warp running maxima / NaN flag (results leave through shared memory: by-reference
                         // results would be promoted to registers that are reserved along the whole call chain)
 };
@@ -857,9 +891,39 @@ __device__ __noinline__ void score_batch(const ScoreArgs& A) {
   double best = 0.0;
   int bestIdx = -1, sawNan = 0;
   PruneCtx pc;
-  pc.bestS = A.bestS; pc.h1 = 0; pc.validMask = 0;
+  pc.bestS = A.bestS; pc.h1 = 0; pc.validMask = 0; pc.pts = 0;
+  int ptsAll = 0;
 #pragma unroll
   for (int g = 0; g < GRP; ++g) pc.a1[g] = 0.0;
+  if (PRUNE && A.t0 == 0) {
+    // Warm start of the incumbent: every warp sums one hypothesis next to the centre of the search (the coarse
+    // winner: rotations mid-1 .. mid+1, offsets 0 and +-1 cell) with its lanes striding over the points -- not in
+    // numpy's order, so the sum minus a margin far above its rounding error (<= 512 * 2^-53 * |sum|) is used: a valid
+    // lower bound of that hypothesis' exact score, hence of the maximum.  Hopeless hypotheses are then dropped at
+    // their first bound check instead of running until the first exact score exists.
+    const int lane = tid & 31, warp = tid >> 5, mid = A.nt >> 1;
+    for (int c = warp; c < 15; c += NWC) {
+      const int tl = min(max(mid + (c % 3) - 1, 0), A.nt - 1), o = c / 3;
+      const int step = A.nHalf > 0 ? 1 : 0;
+      const int da = step * ((o == 3) - (o == 4)), db = step * ((o == 1) - (o == 2));
+      const unsigned off = (unsigned)((db << 16) + da);
+      const unsigned* list = lists + tl * A.Kpad;
+      const int n = cnts[tl];
+      double sum = 0.0;
+      for (int k = lane; k < n; k += 32) {
+        const unsigned sxy = list[k] + off, xx = sxy >> 16, yy = sxy & 0xffffu;
+        const bool on = (dil[yy * A.words + (xx >> 5)] >> (xx & 31u)) & 1u;
+        sum += on ? __ldca(Pf + (yy * A.Pp + xx)) : A.B2;
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(FULL, sum, d);
+      if (lane == 0) {
+        const double lb = sum - 1e-9 * (1.0 + fabs(sum));          // scores are <= 0: the larger double has the smaller bit pattern
+        atomicMin(reinterpret_cast<unsigned long long*>(A.bestP), (unsigned long long)__double_as_longlong(lb));
+      }
+    }
+    csync();
+  }
   for (int q = tid; q < nq; q += NTC) {
     int tl = q / perTheta;
     const int rem0 = q - tl * perTheta;
@@ -887,6 +951,7 @@ __device__ __noinline__ void score_batch(const ScoreArgs& A) {
       f.P = Pf; f.B2 = A.B2; f.pitch = A.Pp; f.words = A.words;
       f.off = (unsigned)(((b0 - A.nHalf) << 16) + (a - A.nHalf));
       pc.validMask = (b0 + 1 < nOff) ? 3 : 1;
+      ptsAll += cnts[tl];
       pruned = pairwise_g<PRUNE>(f, cnts[tl], sc, pc);
     }
     if (pruned) continue;
@@ -909,6 +974,10 @@ __device__ __noinline__ void score_batch(const ScoreArgs& A) {
         }
       }
     }
+  }
+  if (PRUNE && A.ptsSlot) {
+    const int a = __reduce_add_sync(FULL, pc.pts), b = __reduce_add_sync(FULL, ptsAll);
+    if ((tid & 31) == 0) { atomicAdd((unsigned long long*)A.ptsSlot, (unsigned long long)a); atomicAdd((unsigned long long*)A.ptsSlot + 1, (unsigned long long)b); }
   }
   // first maximum in C order over the warp, merged into the warp's running maximum of the earlier batches
 #pragma unroll
@@ -1559,6 +1628,7 @@ __device__ __noinline__ void correlate_phase(const MatchParams& P, CtaShared& sh
   if (tid == 0) bs.nanFlag = 0;                                          // read after the barriers below
   ScoreArgs SA;
   SA.bs = &bs;
+  SA.ptsSlot = P.dbgCycles ? P.dbgCycles + (size_t)blockIdx.x * 48 + 44 : nullptr;
   SA.gslot = gslot; SA.rv = rv; SA.tw = tw; SA.dvol = dvol; SA.B2 = S.B2; SA.thr = thr;
   SA.gP = S.gP; SA.gDil = S.gDil; SA.gScores = S.gScores;
   SA.oLists = S.oLists; SA.oCnt = S.oCnt; SA.oP = S.oP; SA.oDil = S.oDil; SA.oScores = S.oScores;
@@ -1883,6 +1953,7 @@ struct CorrParams {
 };
 
 struct FetchGlobalDense {
+  static constexpr bool kWide = false;
   const unsigned* list;
   const double* base;
   unsigned off;

@@ -17,7 +17,9 @@ from slam_2d_lidar_scan_b200 import synthetic  # noqa: E402
 workload = sys.argv[1] if len(sys.argv) > 1 else "c3"
 spec = synthetic.config(workload)
 n = int(sys.argv[2]) if len(sys.argv) > 2 else spec["N"]
-scene = synthetic.make_scene(seed=0, steps=8, K=spec["K"], fov=spec["og"][4], unit=spec["og"][3])
+after = int(sys.argv[3]) if len(sys.argv) > 3 else 4        # steps before the two measured ones (maps fill up with time)
+stride = float(sys.argv[4]) if len(sys.argv) > 4 else 0.25
+scene = synthetic.make_scene(seed=0, steps=after + 4, K=spec["K"], fov=spec["og"][4], unit=spec["og"][3], stride=stride)
 np.random.seed(0)
 pf = S.ParticleFilter(n, spec["og"], spec["sm"])
 pf.keepTrajectory = False
@@ -32,8 +34,9 @@ plan = (nat.C.c_int * 8)()
 for s in range(2):
     nat.lib.slam_matcher_plan(pf.engine.handle, s, nat.C.byref(plan))
     print("stage", s, "PInSmem,scoresInSmem,bitsInSmem,R,TB,Ppitch,smemBytes,slotKB =", list(plan))
-for count, fr in enumerate(scene["frames"][:6], start=1):
-    if count == 5:
+pf.ignoreMissingHeading = True
+for count, fr in enumerate(scene["frames"][:after + 2], start=1):
+    if count == after + 1:
         nat.lib.slam_matcher_set_debug(pf.engine.handle, cyc.data_ptr(), 0)
         cyc.zero_()
         torch.cuda.synchronize()
@@ -56,6 +59,8 @@ sub = ["B clear+maps", "C scatter", "C transpose", "-", "D1 dilate", "D2 blur (o
 for st in range(2):
     print("  sub-phases %s: " % ("coarse" if st == 0 else "fine") + ", ".join("%s %.0f" % (sub[k], per[16 + 16 * st + k]) for k in range(12) if sub[k] != "-"))
 print("cold start per CTA: compute-side pack %.0f, then wait for the stream warps %.0f cycles" % (c[:, 29].sum() / (2 * ctas), c[:, 28].sum() / (2 * ctas)))
+print("fine branch-and-bound: %.1f %% of the points of the evaluated hypotheses were gathered" % (100.0 * c[:, 44].sum() / max(c[:, 45].sum(), 1)))
+print("fine field: %.0f active tiles, %.0f active cells per particle" % (c[:, 46].sum() / (2 * n), c[:, 47].sum() / (2 * n)))
 per[16:] = 0
 print("stream warp: TMA wait %.0f, pack %.0f, bitmap-free wait %.0f cycles/particle" % (per[7], per[14], per[15]))
 per[7] = per[14] = per[15] = 0
