@@ -1484,11 +1484,12 @@ __device__ __noinline__ void window_phase(const MatchParams& P, CtaShared& sh, i
         const int row = 32 * rb + lane;
         const unsigned w = row < Wy ? bits[row * words + wb] : 0u;
         if (__ballot_sync(FULL, w != 0u) == 0u) continue;          // bitsT was cleared in B
-        unsigned out = 0u;
+        // 32x32 bit-matrix transpose across the warp: five butterfly exchanges (lane k <-> k ^ j swap sub-blocks)
+        unsigned out = w;
 #pragma unroll
-        for (int kk = 0; kk < 32; ++kk) {
-          const unsigned m = __ballot_sync(FULL, (w >> kk) & 1u);
-          if (lane == kk) out = m;
+        for (int j = 16, m = 0x0000ffff; j; j >>= 1, m ^= (m << j)) {
+          const unsigned y = __shfl_xor_sync(FULL, out, j);
+          out = (lane & j) ? (((y >> j) & (unsigned)m) | (out & ~(unsigned)m)) : ((out & (unsigned)m) | ((y << j) & ~(unsigned)m));
         }
         const int col = 32 * wb + lane;
         if (col < Wx) bitsT[col * WT + rb] = out;

@@ -17,6 +17,13 @@ col = {k: i for i, k in enumerate(h)}
 
 
 def val(name):
+    if name not in col:
+        hits = [k for k in col if k.endswith(name)]
+        if not hits:
+            return None
+        name = hits[0]
+    if v[col[name]] in ("", "n/a"):
+        return None
     x, unit = float(v[col[name]].replace(",", "")), u[col[name]]
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ms": 1, "us": 1e-3, "ns": 1e-6, "s": 1e3, "%": 1, "": 1,
              "inst": 1, "cycle": 1}
@@ -28,7 +35,7 @@ out = {
     "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
     "dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
     "gpu_time_ms_under_ncu": val("gpu__time_duration.sum"),
-    "issue_active_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active") if "smsp__issue_active.avg.pct_of_peak_sustained_active" in col else None,
+    "issue_active_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
     "warps_active_pct": val("sm__warps_active.avg.pct_of_peak_sustained_active"),
     "dram_throughput_pct": val("dram__throughput.avg.pct_of_peak_sustained_elapsed"),
     "fp64_pipe_pct": val("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
