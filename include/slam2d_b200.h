@@ -103,6 +103,9 @@ int slam_matcher_create(const slam_geometry* geom, const slam_matcher_desc* desc
 void slam_matcher_destroy(slam_matcher* m);
 /* Device scratch the caller must provide to slam_match_scan (likelihood fields in flight; L2-resident). */
 size_t slam_matcher_workspace_bytes(const slam_matcher* m);
+/* The same for a call with N particles: one slot per CTA that gets a particle (a standalone ScanMatcher, N = 1, needs a
+ * single slot instead of one per SM). */
+size_t slam_matcher_workspace_bytes_n(const slam_matcher* m, int32_t N);
 /* Side of the largest field / number of hypotheses per stage (stage 0 = coarse, 1 = fine). */
 int slam_matcher_field_side(const slam_matcher* m, int stage);
 int slam_matcher_num_poses(const slam_matcher* m, int stage);

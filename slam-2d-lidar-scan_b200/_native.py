@@ -52,6 +52,7 @@ SYMBOLS = {
     "slam_matcher_create": (C.c_int, [C.POINTER(Geometry), C.POINTER(MatcherDesc), C.POINTER(_V)]),
     "slam_matcher_destroy": (None, [_V]),
     "slam_matcher_workspace_bytes": (_Z, [_V]),
+    "slam_matcher_workspace_bytes_n": (_Z, [_V, _I]),
     "slam_matcher_field_side": (C.c_int, [_V, C.c_int]),
     "slam_matcher_num_poses": (C.c_int, [_V, C.c_int]),
     "slam_match_scan": (C.c_int, [_V, _V, _I, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _Z, C.POINTER(MatchDebug), _V]),

@@ -2501,6 +2501,10 @@ extern "C" void slam_matcher_destroy(slam_matcher* m) {
 }
 
 extern "C" size_t slam_matcher_workspace_bytes(const slam_matcher* m) { return m ? m->workspaceBytes : 0; }
+extern "C" size_t slam_matcher_workspace_bytes_n(const slam_matcher* m, int32_t N) {
+  if (!m || N <= 0) return 0;
+  return m->P.slotBytes * (size_t)std::min((int)N, m->numCtas) + 256;      // one slot per CTA that gets a particle
+}
 extern "C" int slam_matcher_field_side(const slam_matcher* m, int stage) { return m->P.st[stage & 1].Wmax; }
 extern "C" int slam_matcher_num_poses(const slam_matcher* m, int stage) { return m->P.st[stage & 1].nPoses; }
 
@@ -2539,7 +2543,8 @@ extern "C" int slam_match_scan_slots(slam_matcher* m, const float* d_grid, const
   if (!m || !d_grid || !d_ranges || !d_estPose || !d_rv || !d_outPose || !d_outConf || !d_outIdx || !d_status)
     return fail(SLAM_E_BADARG, "slam_match_scan: null argument");
   if (N <= 0) return 0;
-  if (!d_workspace || workspaceBytes < m->workspaceBytes) return fail(SLAM_E_BADARG, "slam_match_scan: workspace too small");
+  if (!d_workspace || workspaceBytes < slam_matcher_workspace_bytes_n(m, N))
+    return fail(SLAM_E_BADARG, "slam_match_scan: workspace too small (slam_matcher_workspace_bytes_n)");
   MatchParams P = m->P;
   P.N = N;
   P.grid = d_grid; P.slots = d_slots; P.ranges = d_ranges; P.estPose = d_estPose; P.rv = d_rv; P.tw = d_tw; P.uniforms = d_uniforms;
@@ -2615,7 +2620,8 @@ extern "C" int slam_field_build(slam_matcher* m, int32_t stage, const float* d_g
   if (!m || !d_grid || !d_centre || !d_prob || !d_probDims || !d_status || (stage != 0 && stage != 1))
     return fail(SLAM_E_BADARG, "slam_field_build: bad argument");
   if (N <= 0) return 0;
-  if (!d_workspace || workspaceBytes < m->workspaceBytes) return fail(SLAM_E_BADARG, "slam_field_build: workspace too small");
+  if (!d_workspace || workspaceBytes < slam_matcher_workspace_bytes_n(m, N))
+    return fail(SLAM_E_BADARG, "slam_field_build: workspace too small (slam_matcher_workspace_bytes_n)");
   MatchParams P = m->P;
   P.N = N;
   P.fieldOnlyStage = stage;

@@ -113,8 +113,9 @@ class ShardedParticleFilter:
         pf, n, nL = self.local, self.numParticles, self.hi - self.lo
         dev = pf.geom.device
         u = torch.from_numpy(np.random.random_sample(n)).to(dev)                  # same draw on every rank
-        nat.check(nat.lib.slam_resample_indices(n, self._w.data_ptr(), u.data_ptr(), self._cdf.data_ptr(),
-                                                self._ridx.data_ptr(), _stream(dev)))
+        with torch.cuda.device(dev):
+            nat.check(nat.lib.slam_resample_indices(n, self._w.data_ptr(), u.data_ptr(), self._cdf.data_ptr(),
+                                                    self._ridx.data_ptr(), _stream(dev)))
         idx = self._ridx.cpu().numpy()
         plan = plan_resample_transfers(idx, nL, self.world)[self.rank]
         hist = torch.stack(pf._traj, 0) if pf._traj else None                    # [T][nL][2] matched positions so far

@@ -95,8 +95,20 @@ class MatcherEngine:
             nat.check(nat.lib.slam_matcher_create(C.byref(geom.c), C.byref(desc), C.byref(h)))
         self.handle = h
         self.nOffC = 2 * self.stageInfo[0]["nHalf"] + 1
-        self.workspace = torch.empty(nat.lib.slam_matcher_workspace_bytes(h), dtype=torch.uint8, device=geom.device)
+        self._workspace = None               # device scratch, sized for the largest batch seen so far
         self.zeroRv = torch.zeros(self.nOffC * self.nOffC, dtype=torch.float64, device=geom.device)
+
+    def workspace_for(self, n):
+        """Scratch for a call with n particles (one slot per CTA that gets a particle; a standalone matcher needs one)."""
+        need = nat.lib.slam_matcher_workspace_bytes_n(self.handle, n)
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.geom.device)
+        return self._workspace
+
+    @property
+    def workspace(self):
+        """Scratch large enough for any batch (stage-level entries, slam_correlate)."""
+        return self.workspace_for(1 << 30)
 
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
@@ -156,13 +168,13 @@ class MatcherEngine:
         Status bits are OR-ed into d_status (sticky).  ``slots`` (int32 [n]): particle p reads lattice slots[p] of
         ``grids`` (all lattices of the filter) instead of lattice p."""
         dev = self.geom.device
+        ws = self.workspace_for(n)
         with torch.cuda.device(dev):
             nat.check(nat.lib.slam_match_scan_slots(
                 self.handle, grids.data_ptr(), _ptr(slots), grids.shape[0] if slots is not None else n, n,
                 d_ranges.data_ptr(), d_estPose.data_ptr(), d_rv.data_ptr(), _ptr(d_tw),
                 _ptr(d_uniforms), d_outPose.data_ptr(), d_outConf.data_ptr(), d_outIdx.data_ptr(), d_status.data_ptr(),
-                self.workspace.data_ptr(), self.workspace.numel(), C.byref(debug) if debug is not None else None,
-                _stream(dev)))
+                ws.data_ptr(), ws.numel(), C.byref(debug) if debug is not None else None, _stream(dev)))
 
     def volume_shape(self, stage):
         n = 2 * self.stageInfo[stage]["nHalf"] + 1

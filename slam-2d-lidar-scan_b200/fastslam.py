@@ -230,8 +230,9 @@ class ParticleFilter:
         n, dev = self.numParticles, self.geom.device
         u = torch.from_numpy(np.random.random_sample(n)).to(dev)
         st = _stream(dev)
-        nat.check(nat.lib.slam_resample_indices(n, self.weights.data_ptr(), u.data_ptr(), self._cdf.data_ptr(),
-                                                self._ridx.data_ptr(), st))
+        with torch.cuda.device(dev):
+            nat.check(nat.lib.slam_resample_indices(n, self.weights.data_ptr(), u.data_ptr(), self._cdf.data_ptr(),
+                                                    self._ridx.data_ptr(), st))
         idx = self._ridx.to(torch.int64)
         hidx = idx.cpu().tolist()
         # lattices: ownership moves with the slot table; only the extra copies of multiply-chosen particles are copied

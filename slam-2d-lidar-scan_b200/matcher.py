@@ -136,10 +136,11 @@ class ScanMatcher:
         dims = torch.zeros(2, dtype=torch.int32, device=dev)
         self._est.copy_(torch.tensor([estimatedX, estimatedY, 0.0], dtype=torch.float64))
         self._status.zero_()
+        ws = eng.workspace_for(1)
         with torch.cuda.device(dev):
             nat.check(nat.lib.slam_field_build(eng.handle, s, self.og.device_grid.data_ptr(), 1, self._est.data_ptr(),
                                                prob.data_ptr(), dims.data_ptr(), self._status.data_ptr(),
-                                               eng.workspace.data_ptr(), eng.workspace.numel(), _stream(dev)))
+                                               ws.data_ptr(), ws.numel(), _stream(dev)))
         raise_for_status(int(self._status.item()))
         rows, cols = (int(v) for v in dims.cpu())
         return xRangeList, yRangeList, prob[:rows, :cols].cpu().numpy()
@@ -227,12 +228,13 @@ class ScanMatcher:
         vol = torch.zeros(poses, **f64)
         outIdx = torch.zeros(3, dtype=torch.int32, device=dev)
         self._status.zero_()
+        ws = eng.workspace_for(1)
         with torch.cuda.device(dev):
             nat.check(nat.lib.slam_correlate(
                 eng.handle, s, 1, prob.data_ptr(), dims.data_ptr(), self._ranges.data_ptr(), centre.data_ptr(),
                 origin.data_ptr(), 0 if rv is None else rv.data_ptr(), 0 if tw is None else tw.data_ptr(),
                 0 if u is None else u.data_ptr(), vol.data_ptr(), outIdx.data_ptr(), self._outConf.data_ptr(),
-                self._status.data_ptr(), eng.workspace.data_ptr(), eng.workspace.numel(), _stream(dev)))
+                self._status.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
         confidence = float(self._outConf.item())
         raise_for_status(int(self._status.item()))
         it, iy, ix = (int(v) for v in outIdx.cpu())
