@@ -189,6 +189,7 @@ constexpr int GRP = 2;   // adjacent x offsets handled by one thread (share the 
 // Dense field (coarse stage, shared memory): GRP consecutive cells of one row per point.  32-bit shared addressing.
 struct FetchDense {
   static constexpr bool kWide = false;   // shared-memory gathers: 8 points (16 loads) in flight are enough
+  static constexpr bool kKeys8 = true;   // the phase is bound by shared-memory wavefronts: 8 keys in two 16-byte loads
   unsigned listS;        // shared address of the sorted unique keys (x << 16 | y)
   unsigned baseS;        // shared address of the field
   unsigned off;          // (dx << 16) + dy, added to the key in one go
@@ -204,6 +205,12 @@ struct FetchDense {
 #pragma unroll
     for (int g = 0; g < GRP; ++g) v[g] = lds_f64(a + 8u * g);
   }
+  __device__ __forceinline__ void get8(int k, double (&v)[8][GRP]) const {
+    unsigned key[8];
+    keys8(k, key);
+#pragma unroll
+    for (int l = 0; l < 8; ++l) get_key(key[l], v[l]);
+  }
   __device__ __forceinline__ void get(int k, double (&v)[GRP]) const { get_key(lds_u32(listS + 4u * k), v); }
 };
 
@@ -213,6 +220,7 @@ struct FetchDense {
 template <bool FAST>
 struct FetchGated {
   static constexpr bool kWide = true;    // L2-latency gathers: 16 points (32 predicated loads) in flight per thread
+  static constexpr bool kKeys8 = false;
   const unsigned* list;
   const unsigned* dil;   // activity bitmap [rows][words], last word of every row always zero
   unsigned listS, dilS;  // shared addresses of the same (FAST plan)
@@ -283,8 +291,12 @@ __device__ __forceinline__ bool leaf_sum_g(const F& f, int off, int n, double (&
     return false;
   }
   double r[8][GRP];
+  if constexpr (F::kKeys8) {
+    f.get8(off, r);
+  } else {
 #pragma unroll
-  for (int l = 0; l < 8; ++l) f.get(off + l, r[l]);
+    for (int l = 0; l < 8; ++l) f.get(off + l, r[l]);
+  }
   const int m = n - (n & 7);
   int i = 8;
   auto bound_below_incumbent = [&]() {      // pairwise tree over the CURRENT lane sums: an upper bound of the final score
@@ -321,8 +333,12 @@ __device__ __forceinline__ bool leaf_sum_g(const F& f, int off, int n, double (&
   }
   for (; i < m; i += 8) {
     double v[8][GRP];
+    if constexpr (F::kKeys8) {
+      f.get8(off + i, v);
+    } else {
 #pragma unroll
-    for (int l = 0; l < 8; ++l) f.get(off + i + l, v[l]);       // eight independent gathers in flight
+      for (int l = 0; l < 8; ++l) f.get(off + i + l, v[l]);     // eight independent gathers in flight
+    }
     if (PRUNE) pc.pts += 8;
 #pragma unroll
     for (int l = 0; l < 8; ++l) {
@@ -495,6 +511,7 @@ struct BlockScratch {
   double wbest[NWC];               // per-warp first maximum of the score volume so far (merged batch by batch) ...
   int wbestIdx[NWC];               // ... and its flat index; -1 = none yet
   int nanFlag;                     // a NaN score was seen
+  int taskCounter;                 // next 32-task chunk of the score phase (warps fetch chunks dynamically)
   int ibcast[8];
   unsigned maskA[64], maskB[64];   // per union-bitmap word: window columns whose index-map offset is D / D-1
 };
@@ -780,7 +797,6 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           if ((act4 >> e) & 1u) {
-            if (!anyInactive) mn = fmin(mn, val[e]);    // otherwise probMin == B2 is already known
             out[e] = val[e] > thr ? 0.0 : val[e];       // clamp (:44)
           }
         }
@@ -847,6 +863,14 @@ __device__ __noinline__ void blur_stage(const StageDev& S, unsigned char* gslot,
       __syncwarp();
     }
   }
+  }
+  if (RT > 0 && !anyInactive) {
+    // no background cell at all (tiny windows): probMin is not known in advance -- take it from the finished field
+    csync();
+    for (int i = tid; i < Wy * Wx; i += NTC) {
+      const int yy = i / Wx, xx = i - yy * Wx;
+      mn = fmin(mn, Pf[(size_t)yy * Pp + xx]);
+    }
   }
   sc.mark(5);      // D2 (own tiles; the wait for the other warps is accounted to the caller)
   if (subSlots && !DENSE && lane == 0) {      // profiling: active tiles / cells of the fine field
@@ -924,7 +948,16 @@ __device__ __noinline__ void score_batch(const ScoreArgs& A) {
     }
     csync();
   }
-  for (int q = tid; q < nq; q += NTC) {
+  // Warps fetch 32-task chunks from a shared counter: with the branch-and-bound a chunk next to the optimum costs
+  // several times a pruned one, and a static split leaves warps waiting at the barrier that ends the phase.
+  const int lane_ = tid & 31;
+  for (;;) {
+    int chunk = 0;
+    if (lane_ == 0) chunk = atomicAdd(&A.bs->taskCounter, 1);
+    chunk = __shfl_sync(FULL, chunk, 0);
+    if (chunk * 32 >= nq) break;
+    const int q = chunk * 32 + lane_;
+    if (q >= nq) continue;
     int tl = q / perTheta;
     const int rem0 = q - tl * perTheta;
     if (PRUNE) {      // most promising rotations first (centre of the batch outwards): good incumbents early
@@ -1650,6 +1683,7 @@ __device__ __noinline__ void correlate_phase(const MatchParams& P, CtaShared& sh
     LA.nt = nt; LA.t0 = t0;
     if (S.E == 8) lists_batch<8>(LA, status);
     else lists_batch<16>(LA, status);
+    if (tid == 0) bs.taskCounter = 0;          // chunk counter of the score phase, published by the barrier below
     csync();
     if (cyc && tid == 0) { long long t = clock64(); cyc[3] += t; cyc[4] -= t; }
     SA.nt = nt; SA.t0 = t0;
@@ -1721,13 +1755,25 @@ __device__ __noinline__ void select_phase(const MatchParams& P, CtaShared& sh, i
       for (int i = (n < 8 ? 0 : m); i < n; ++i) r = dadd(r, scores[off + i]);     // n < 8: plain sequential sum; else the tail
       if (valid && l == 0) leafSum[g] = r;
     }
+    // operands of the combine tree (global tables): fetched by warp 0 before the barrier, not level by level after it
+    int2 opA = make_int2(0, 0), opB = make_int2(0, 0);
+    const bool opsInRegs = S.nOps <= 64;
+    if (warp == 0 && opsInRegs) {
+      if (lane < S.nOps) opA = S.ops[lane];
+      if (lane + 32 < S.nOps) opB = S.ops[lane + 32];
+    }
     csync();
     if (warp == 0) {   // combine the leaves along numpy's recursion tree, one tree level at a time
       for (int l = 0; l < S.nLevels; ++l) {
-        const int o1 = S.levelStart[l + 1];
-        for (int o = S.levelStart[l] + lane; o < o1; o += 32) {
-          const int2 op = S.ops[o];
-          leafSum[S.nLeaves + o] = dadd(leafSum[op.x], leafSum[op.y]);
+        const int o0 = S.levelStart[l], o1 = S.levelStart[l + 1];
+        if (opsInRegs) {
+          if (lane >= o0 && lane < o1) leafSum[S.nLeaves + lane] = dadd(leafSum[opA.x], leafSum[opA.y]);
+          if (lane + 32 >= o0 && lane + 32 < o1) leafSum[S.nLeaves + lane + 32] = dadd(leafSum[opB.x], leafSum[opB.y]);
+        } else {
+          for (int o = o0 + lane; o < o1; o += 32) {
+            const int2 op = S.ops[o];
+            leafSum[S.nLeaves + o] = dadd(leafSum[op.x], leafSum[op.y]);
+          }
         }
         __syncwarp();
       }
@@ -1955,6 +2001,7 @@ struct CorrParams {
 
 struct FetchGlobalDense {
   static constexpr bool kWide = false;
+  static constexpr bool kKeys8 = false;
   const unsigned* list;
   const double* base;
   unsigned off;
