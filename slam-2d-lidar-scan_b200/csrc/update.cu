@@ -7,12 +7,15 @@
 // where the map index of a local cell is rint((pose + local - mapLim0)/unit) and numpy's fancy `+=` applies
 // once per distinct map cell per statement.
 //
-// Here the loop is inverted (owner computes, no atomics): sectors of distinct beams are disjoint, so a local
-// cell belongs to at most one beam.  A per-particle preparation pass evaluates the float64 index maps of the
-// L local columns / rows; when both are pure shifts (always true for poses emitted by the matcher, which sit
-// on the lattice) every local cell owns exactly one map cell and the fast kernel runs; otherwise (pose exactly
-// half a cell off the lattice, where rint's half-to-even collapses neighbours) the general map-cell-owned
-// kernel reproduces the per-statement union semantics.
+// Here the loop is inverted (owner computes): sectors of distinct beams are disjoint, so a local cell belongs to at
+// most one beam.  A per-particle preparation pass evaluates the float64 index maps of the L local columns / rows;
+// when both are pure shifts (always true for poses emitted by the matcher, which sit on the lattice) every local
+// cell owns exactly one map cell and the fast path runs; otherwise (pose exactly half a cell off the lattice, where
+// rint's half-to-even collapses neighbours) the general map-cell-owned path reproduces the per-statement union
+// semantics.  Three launches per call: prep -> group (particles by sector shift) -> apply (+ general path).
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace slam {
@@ -28,6 +31,13 @@ struct UpdParams {
   int* status;
   const int* slots;   // physical lattice of particle p (null: p itself) -- copy-elided resampling keeps a slot table
   double* reach;      // [1] largest radius any beam of this scan can touch (empty or hit), written by the prep kernel
+  // particles grouped by sector shift (update_group_kernel): all particles of a group see the same empty / hit flags
+  int* hdr;           // [0] number of work items, [1] first sector of the union of the beam fans, [2] its length
+  int* hist;          // [numSpokes] particles per sector shift, then the write cursor of each shift's group
+  int4* items;        // work items (sectorShift, first slot in gbase / plist, particles (<= UPD_ITEM), all inside the map)
+  long long* gbase;   // per grouped slot: cell index of the patch origin inside the lattice batch
+  int* plist;         // per grouped slot: particle
+  unsigned char* ginside;   // per grouped slot: the whole patch lies inside the lattice
 };
 
 __device__ __forceinline__ size_t lattice_of(const UpdParams& P, int p) { return (size_t)(P.slots ? P.slots[p] : p); }
@@ -55,13 +65,23 @@ __global__ void update_prep_kernel(UpdParams P) {
   }
   if (warp >= P.N) return;
   const double x = P.pose[3 * warp], y = P.pose[3 * warp + 1], th = P.pose[3 * warp + 2];
-  const int sx = (int)rint(ddiv(dsub(dadd(x, P.axis[0]), P.mapX0), P.unit));
-  const int sy = (int)rint(ddiv(dsub(dadd(y, P.axis[0]), P.mapY0), P.unit));
+  const double a0 = P.axis[0];
+  const int sx = (int)rint(ddiv(dsub(dadd(x, a0), P.mapX0), P.unit));
+  const int sy = (int)rint(ddiv(dsub(dadd(y, a0), P.mapY0), P.unit));
   bool pure = true;
-  for (int l = lane; l < P.L; l += 32) {
-    const int ix = (int)rint(ddiv(dsub(dadd(x, P.axis[l]), P.mapX0), P.unit));
-    const int iy = (int)rint(ddiv(dsub(dadd(y, P.axis[l]), P.mapY0), P.unit));
-    if (ix != sx + l || iy != sy + l) pure = false;
+  for (int l0 = lane; l0 < P.L; l0 += 32 * 8) {      // 8 independent axis loads in flight per lane
+    double ax[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ax[j] = l0 + 32 * j < P.L ? __ldg(P.axis + l0 + 32 * j) : 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int l = l0 + 32 * j;
+      if (l < P.L) {
+        const int ix = (int)rint(ddiv(dsub(dadd(x, ax[j]), P.mapX0), P.unit));
+        const int iy = (int)rint(ddiv(dsub(dadd(y, ax[j]), P.mapY0), P.unit));
+        if (ix != sx + l || iy != sy + l) pure = false;
+      }
+    }
   }
   pure = __all_sync(0xffffffffu, pure);
   if (lane == 0) {
@@ -70,7 +90,6 @@ __global__ void update_prep_kernel(UpdParams P) {
     int shift = (P.start + off) % P.numSpokes;          // beam i looks at sector (shift + i) % numSpokes (:134)
     if (shift < 0) shift += P.numSpokes;
     P.prep[warp] = make_int4(sx, sy, shift, pure ? UPD_PURE : 0);
-    if (!pure) P.slow[1 + atomicAdd(&P.slow[0], 1)] = warp;
   }
 }
 
@@ -79,142 +98,166 @@ __device__ __forceinline__ int beam_of(int sector, int shift, int numSpokes) {
   return b < 0 ? b + numSpokes : b;              // sector, shift in [0, numSpokes)
 }
 
-// Fast path: thread owns a lidar-local cell and loops over a chunk of particles.  All particles share the scan; only
-// the heading (quantised to whole spokes, :131) differs, so a chunk of 32 particles has a handful of DISTINCT sector
-// shifts: the cell's empty / hit flags are evaluated once per distinct shift (2 bits each in a 64-bit mask) and the
-// particle loop only does the read-modify-writes.  Blocks whose cells lie outside the union of the chunk's beam fans
-// or beyond the reach of the scan leave before the interval tables are even built.
-constexpr int UPD_CHUNK = 32;
-__global__ void __launch_bounds__(256) update_fast_kernel(UpdParams P) {
-  // per-sector interval tables of this scan: a cell of beam b is seen-empty iff r < loE[b] and hit iff lo[b] < r < hi[b]
-  // (:138-143); sectors outside the fan get intervals that are never satisfied, so no beam < K test is needed
-  extern __shared__ double s_tab[];
-  double* s_loE = s_tab;
-  double* s_lo = s_tab + P.numSpokes;
-  double* s_hi = s_tab + 2 * P.numSpokes;
-  __shared__ int4 s_prep[UPD_CHUNK];
-  __shared__ size_t s_lat[UPD_CHUNK];
-  __shared__ int s_fan[2];      // sectors any particle of the chunk can look at: [start, start + length) mod numSpokes
-  __shared__ int s_dshift[UPD_CHUNK], s_didx[UPD_CHUNK], s_nd;     // distinct shifts, particle -> index into them
-  const int p0 = blockIdx.y * UPD_CHUNK;
-  const int np = min(UPD_CHUNK, P.N - p0);
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x, nS = P.numSpokes;
-    int4 pr = make_int4(0, 0, 0, 0);
-    if (lane < np) {
-      pr = P.prep[p0 + lane];
-      s_prep[lane] = pr;
-      s_lat[lane] = lattice_of(P, p0 + lane);
-    }
-    // union of the particles' beam fans (headings of a chunk differ by a few spokes)
-    const int ref = __shfl_sync(0xffffffffu, pr.z, 0);
-    int d = lane < np ? pr.z - ref : 0;
-    d = ((d + nS / 2) % nS + nS) % nS - nS / 2;        // signed circular distance to the first particle's shift
-    const int dmin = __reduce_min_sync(0xffffffffu, d), dmax = __reduce_max_sync(0xffffffffu, d);
-    if (lane == 0) { s_fan[0] = ((ref + dmin) % nS + nS) % nS; s_fan[1] = P.K + (dmax - dmin); }
-    // distinct shifts: the lowest lane of every group of equal shifts is its leader
-    const unsigned grp = __match_any_sync(0xffffffffu, lane < np ? pr.z : -1 - lane);
-    const bool leader = lane < np && (__ffs(grp) - 1) == lane;
-    const unsigned leaders = __ballot_sync(0xffffffffu, leader);
-    if (leader) s_dshift[__popc(leaders & ((1u << lane) - 1u))] = pr.z;
-    if (lane < np) s_didx[lane] = __popc(leaders & ((1u << (__ffs(grp) - 1)) - 1u));
-    if (lane == 0) s_nd = __popc(leaders);
+// Particles grouped by sector shift.  All particles share the scan and differ only in the heading, quantised to whole
+// spokes (:131): a population has a few dozen DISTINCT shifts, and every particle of a shift group sees the same empty /
+// hit flag in every lidar-local cell.  One block: histogram over the shifts, compaction of the non-empty ones into work
+// items of <= UPD_ITEM particles, particle slots in group order (patch origin inside the lattice batch, particle id).
+constexpr int UPD_ITEM = 32;
+constexpr int UPD_GROUP_T = 1024;
+__global__ void __launch_bounds__(UPD_GROUP_T) update_group_kernel(UpdParams P) {
+  __shared__ int s_scanA[UPD_GROUP_T / 32], s_scanB[UPD_GROUP_T / 32];
+  __shared__ int s_fanMin, s_fanMax, s_slow;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nS = P.numSpokes;
+  for (int s = tid; s < nS; s += UPD_GROUP_T) P.hist[s] = 0;
+  if (tid == 0) { s_fanMin = 1 << 30; s_fanMax = -(1 << 30); s_slow = 0; }
+  __syncthreads();
+  // histogram + union of the beam fans as a signed circular distance to the first pure particle's shift
+  int ref = -1;
+  for (int p = 0; p < P.N && ref < 0; ++p)        // (uniform, normally one trip)
+    if (P.prep[p].w & UPD_PURE) ref = P.prep[p].z;
+  int dmin = 1 << 30, dmax = -(1 << 30);
+  for (int p = tid; p < P.N; p += UPD_GROUP_T) {
+    const int4 pr = P.prep[p];
+    if (!(pr.w & UPD_PURE)) { P.slow[1 + atomicAdd(&s_slow, 1)] = p; continue; }     // general path (order irrelevant)
+    atomicAdd(&P.hist[pr.z], 1);
+    int d = pr.z - ref;
+    d = ((d + nS / 2) % nS + nS) % nS - nS / 2;
+    dmin = min(dmin, d); dmax = max(dmax, d);
+  }
+  dmin = __reduce_min_sync(0xffffffffu, dmin); dmax = __reduce_max_sync(0xffffffffu, dmax);
+  if (lane == 0 && dmin <= dmax) { atomicMin(&s_fanMin, dmin); atomicMax(&s_fanMax, dmax); }
+  __syncthreads();
+  // exclusive scans over the spokes (a contiguous segment per thread): work items and particle slots before each spoke
+  const int seg = (nS + UPD_GROUP_T - 1) / UPD_GROUP_T;
+  const int s0 = min(tid * seg, nS), s1 = min(s0 + seg, nS);
+  int nItems = 0, nPart = 0;
+  for (int s = s0; s < s1; ++s) { const int c = P.hist[s]; nItems += (c + UPD_ITEM - 1) / UPD_ITEM; nPart += c; }
+  int inclA = nItems, inclB = nPart;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, inclA, d), b = __shfl_up_sync(0xffffffffu, inclB, d);
+    if (lane >= d) { inclA += a; inclB += b; }
+  }
+  if (lane == 31) { s_scanA[warp] = inclA; s_scanB[warp] = inclB; }
+  __syncthreads();
+  int baseA = 0, baseB = 0, totalA = 0;
+  for (int w = 0; w < UPD_GROUP_T / 32; ++w) {
+    if (w < warp) { baseA += s_scanA[w]; baseB += s_scanB[w]; }
+    totalA += s_scanA[w];
+  }
+  int item = baseA + inclA - nItems, slot = baseB + inclB - nPart;
+  for (int s = s0; s < s1; ++s) {
+    const int c = P.hist[s];
+    P.hist[s] = slot;                              // write cursor of this shift's group
+    for (int q = 0; q < c; q += UPD_ITEM) P.items[item++] = make_int4(s, slot + q, min(UPD_ITEM, c - q), 1);
+    slot += c;
+  }
+  if (tid == 0) {
+    P.slow[0] = s_slow;
+    P.hdr[0] = totalA;
+    P.hdr[1] = s_fanMin <= s_fanMax ? ((ref + s_fanMin) % nS + nS) % nS : 0;
+    P.hdr[2] = s_fanMin <= s_fanMax ? P.K + (s_fanMax - s_fanMin) : 0;
   }
   __syncthreads();
+  const long long gstride = (long long)P.G * P.pitch;
+  for (int p = tid; p < P.N; p += UPD_GROUP_T) {
+    const int4 pr = P.prep[p];
+    if (!(pr.w & UPD_PURE)) continue;
+    const int q = atomicAdd(&P.hist[pr.z], 1);     // order inside a group is irrelevant: distinct particles, distinct lattices
+    P.gbase[q] = (long long)lattice_of(P, p) * gstride + (long long)pr.y * P.pitch + pr.x;
+    P.plist[q] = p;
+    P.ginside[q] = (pr.x >= 0 && pr.y >= 0 && pr.x + P.L <= P.G && pr.y + P.L <= P.G) ? 1 : 0;
+  }
+}
+
+// General path (non-pure index maps): thread owns a MAP cell of the patch's bounding box and tests the <= 3x3 local
+// cells that can round onto it; union within a beam, sum across beams.
+__device__ void update_general_one(const UpdParams& P, int p, int* mx, int* my);
+
+// Fast path: a thread owns a lidar-local cell; a block walks over work items (a sector shift + <= UPD_ITEM particles
+// that share it).  The cell's empty / hit flag is evaluated once per item; the particle loop is nothing but
+// fire-and-forget float reductions at the L2 (RED.ADD.F32 / .F32x2), addresses = the particle's patch origin + the
+// cell's offset.  The counts are small integers, so the float adds are exact, and every cell of a lattice is owned by
+// one thread: the result does not depend on the order.  (Measured on c3: read-modify-write with 8 loads in flight per
+// thread 104 -> reductions 90 us; the chunked round-2 kernel that re-evaluated the flags per 32-particle chunk: 144 us.)
+// The blocks of row blockIdx.y == 0 first serve the particles of the general path (normally none).
+constexpr int UPD_NB = 8;
+__global__ void __launch_bounds__(256) update_apply_kernel(UpdParams P) {
+  extern __shared__ double s_tab[];     // per BEAM: seen empty iff r < loE[b], hit iff lo[b] < r < hi[b]  (:138-143)
+  if (blockIdx.y == 0) {
+    const int count = P.slow[0];
+    int* maps = reinterpret_cast<int*>(s_tab);       // mx[L], my[L]
+    for (int q = 0; q < count; ++q) {
+      update_general_one(P, P.slow[1 + q], maps, maps + P.L);
+      __syncthreads();
+    }
+  }
+  double* s_loE = s_tab;
+  double* s_lo = s_tab + P.K;
+  double* s_hi = s_tab + 2 * P.K;
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nS = P.numSpokes;
   int sec = 0;
   double r = 0.0;
   bool alive = cell < P.L * P.L;
-  if (alive) {   // cells no particle of the chunk can touch: outside the union of the fans, or beyond the reach of the scan
+  if (alive) {   // cells no particle can touch: outside the union of the beam fans, or beyond the reach of the scan
     sec = P.sector[cell];
-    int rel = sec - s_fan[0];
-    if (rel < 0) rel += P.numSpokes;
-    alive = rel < s_fan[1];
+    int rel = sec - P.hdr[1];
+    if (rel < 0) rel += nS;
+    alive = rel < P.hdr[2];
     if (alive) {
       r = P.radius[cell];
       alive = r < P.reach[0];
     }
   }
   if (!__syncthreads_or(alive)) return;
-  for (int k = threadIdx.x; k < P.numSpokes; k += blockDim.x) {
-    double loE = -INFINITY, lo = INFINITY, hi = -INFINITY;
-    if (k < P.K) {
-      const double rm = P.ranges[k];
-      lo = dsub(rm, P.wallHalf);
-      hi = dadd(rm, P.wallHalf);
-      if (rm < P.maxRange) loE = lo;
-    }
-    s_loE[k] = loE; s_lo[k] = lo; s_hi[k] = hi;
+  for (int k = threadIdx.x; k < P.K; k += blockDim.x) {
+    const double rm = P.ranges[k];
+    const double lo = dsub(rm, P.wallHalf);
+    s_lo[k] = lo;
+    s_hi[k] = dadd(rm, P.wallHalf);
+    s_loE[k] = rm < P.maxRange ? lo : -INFINITY;
   }
   __syncthreads();
   if (!alive) return;
   const int ly = cell / P.L, lx = cell - ly * P.L;
-  unsigned long long fm = 0ull;       // 2 bits per distinct shift: bit0 seen empty, bit1 hit
-  const int nd = s_nd;
-  for (int d = 0; d < nd; ++d) {
-    const int beam = beam_of(sec, s_dshift[d], P.numSpokes);
-    const unsigned long long f = (r < s_loE[beam] ? 1ull : 0ull) | ((r > s_lo[beam] && r < s_hi[beam]) ? 2ull : 0ull);
-    fm |= f << (2 * d);
-  }
-  if (fm == 0ull) return;
-  const size_t gstride = (size_t)P.G * P.pitch;
-  int bad = 0;
-  // particles of the chunk in groups of 8: all reads of a group are issued before its writes (distinct particles
-  // own distinct lattices, so the read-modify-writes are independent)
-  for (int q0 = 0; q0 < np; q0 += 8) {
-    float2* ptr[8];
-    float2 val[8];
-    unsigned char flag[8];
+  const long long cellOff = (long long)ly * P.pitch + lx;
+  float2* const grid = reinterpret_cast<float2*>(P.grid);
+  const int nItems = P.hdr[0];
+  for (int it = blockIdx.y; it < nItems; it += gridDim.y) {
+    const int4 item = P.items[it];
+    const int beam = beam_of(sec, item.x, nS);
+    if (beam >= P.K) continue;
+    const bool e = r < s_loE[beam], h = r > s_lo[beam] && r < s_hi[beam];
+    if (!e && !h) continue;
+    const long long* gb = P.gbase + item.y;
+    const unsigned char* gi = P.ginside + item.y;
+    const int m = item.z;
+    for (int q0 = 0; q0 < m; q0 += UPD_NB) {
+      float2* ptr[UPD_NB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      flag[j] = 0;
-      ptr[j] = nullptr;
-      const int q = q0 + j;
-      if (q < np) {
-        const int4 pr = s_prep[q];
-        const unsigned char f = (unsigned char)((fm >> (2 * s_didx[q])) & 3ull);
-        if (f && (pr.w & UPD_PURE)) {
-          const int jx = pr.x + lx, jy = pr.y + ly;
-          if (jx < 0 || jy < 0 || jx >= P.G || jy >= P.G) bad = 1;
-          else {
-            flag[j] = f;
-            ptr[j] = (float2*)P.grid + s_lat[q] * gstride + (size_t)jy * P.pitch + jx;
+      for (int j = 0; j < UPD_NB; ++j) {
+        ptr[j] = nullptr;
+        if (q0 + j < m) {
+          const long long b = gb[q0 + j];
+          bool ok = true;
+          if (!gi[q0 + j]) {      // patch not entirely inside the lattice: check this cell
+            const int p = P.plist[item.y + q0 + j];
+            const int4 pr = P.prep[p];
+            const int jx = pr.x + lx, jy = pr.y + ly;
+            ok = jx >= 0 && jy >= 0 && jx < P.G && jy < P.G;
+            if (!ok) atomicOr(&P.status[p], SLAM_ST_SCAN_OUTSIDE_MAP);
           }
+          if (ok) ptr[j] = grid + (b + cellOff);
         }
       }
-    }
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (flag[j]) val[j] = *ptr[j];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (flag[j]) {
-        float2 v = val[j];
-        if (flag[j] & 1) v.y += 1.f;
-        if (flag[j] & 2) { v.x += 2.f; v.y += 2.f; }
-        *ptr[j] = v;
-      }
-  }
-  if (bad) {
-    for (int q = 0; q < np; ++q) {
-      const int4 pr = s_prep[q];
-      const int jx = pr.x + lx, jy = pr.y + ly;
-      if ((pr.w & UPD_PURE) && ((fm >> (2 * s_didx[q])) & 3ull) && (jx < 0 || jy < 0 || jx >= P.G || jy >= P.G))
-        atomicOr(&P.status[p0 + q], SLAM_ST_SCAN_OUTSIDE_MAP);
+      for (int j = 0; j < UPD_NB; ++j)
+        if (ptr[j]) {
+          if (h) atomicAdd(ptr[j], make_float2(2.f, 2.f));       // visited[hit] += 2; total[hit] += 2   (:151-152)
+          else atomicAdd(&ptr[j]->y, 1.f);                       // total[empty] += 1                    (:149)
+        }
     }
-  }
-}
-
-// General path (non-pure index maps): loops over the flagged particles; thread owns a MAP cell of the patch's
-// bounding box and tests the <= 3x3 local cells that can round onto it; union within a beam, sum across beams.
-__device__ void update_general_one(const UpdParams& P, int p, int* mx, int* my);
-
-__global__ void __launch_bounds__(256) update_general_kernel(UpdParams P) {
-  extern __shared__ int s_maps[];   // mx[L], my[L]
-  const int count = P.slow[0];
-  for (int q = 0; q < count; ++q) {
-    update_general_one(P, P.slow[1 + q], s_maps, s_maps + P.L);
-    __syncthreads();
   }
 }
 
@@ -288,9 +331,15 @@ extern "C" int slam_grid_init(const slam_geometry* g, float* d_grid, int32_t N, 
 }
 
 static size_t upd_prep_bytes(int32_t N) { return ((size_t)N * sizeof(int4) + 255) / 256 * 256; }
+static size_t upd_al(size_t v) { return (v + 255) / 256 * 256; }
+constexpr int UPD_MAX_SPOKES = 8192;
+static size_t upd_items_cap(int32_t N) { return (size_t)N + (size_t)N / UPD_ITEM + 2; }   // <= one partial item per distinct shift
 
 extern "C" size_t slam_update_workspace_bytes(int32_t N) {
-  return N <= 0 ? 0 : upd_prep_bytes(N) + 256 + ((size_t)N + 1) * sizeof(int) + 256;
+  if (N <= 0) return 0;
+  return upd_prep_bytes(N) + 256 + upd_al(((size_t)N + 1) * sizeof(int))              // prep records, reach, slow list
+         + 256 + upd_al(UPD_MAX_SPOKES * sizeof(int)) + upd_al(upd_items_cap(N) * sizeof(int4))   // header, histogram, items
+         + upd_al((size_t)N * sizeof(long long)) + upd_al((size_t)N * sizeof(int)) + upd_al((size_t)N) + 256;
 }
 
 extern "C" int slam_update_grid(const slam_geometry* g, float* d_grid, int32_t N, const double* d_ranges,
@@ -305,33 +354,40 @@ extern "C" int slam_update_grid_slots(const slam_geometry* g, float* d_grid, con
   if (!g || !d_grid || !d_ranges || !d_pose || !d_status) return fail(SLAM_E_BADARG, "slam_update_grid: null argument");
   if (N <= 0) return 0;
   if (g->K > SLAM_MAX_BEAMS) return fail(SLAM_E_UNSUPPORTED, "too many beams");
+  if (g->numSpokes > UPD_MAX_SPOKES) return fail(SLAM_E_UNSUPPORTED, "too many bearing sectors (numSpokes > 8192)");
   cudaStream_t st = (cudaStream_t)stream;
-  // caller-provided scratch (no process-global state: several grids / streams / devices may call concurrently):
-  // [N] int4 preparation records + 1 + N ints of slow-path work list
+  // caller-provided scratch (no process-global state: several grids / streams / devices may call concurrently)
   if (!d_workspace || workspaceBytes < slam_update_workspace_bytes(N))
     return fail(SLAM_E_BADARG, "slam_update_grid: workspace too small (slam_update_workspace_bytes)");
-  const size_t prepBytes = upd_prep_bytes(N);
-  unsigned char* scratch = (unsigned char*)(((size_t)d_workspace + 255) / 256 * 256);
-  int4* g_prep = reinterpret_cast<int4*>(scratch);
-  double* g_reach = reinterpret_cast<double*>(scratch + prepBytes);
-  int* g_slow = reinterpret_cast<int*>(scratch + prepBytes + 256);
-  SLAM_CUDA(cudaMemsetAsync(g_slow, 0, sizeof(int), st));
+  unsigned char* w = (unsigned char*)(((size_t)d_workspace + 255) / 256 * 256);
+  auto take = [&](size_t bytes) { unsigned char* q = w; w += upd_al(bytes); return q; };
+  int4* g_prep = reinterpret_cast<int4*>(take(upd_prep_bytes(N)));
+  double* g_reach = reinterpret_cast<double*>(take(256));
+  int* g_slow = reinterpret_cast<int*>(take(((size_t)N + 1) * sizeof(int)));
   UpdParams P;
+  P.hdr = reinterpret_cast<int*>(take(256));
+  P.hist = reinterpret_cast<int*>(take(UPD_MAX_SPOKES * sizeof(int)));
+  P.items = reinterpret_cast<int4*>(take(upd_items_cap(N) * sizeof(int4)));
+  P.gbase = reinterpret_cast<long long*>(take((size_t)N * sizeof(long long)));
+  P.plist = reinterpret_cast<int*>(take((size_t)N * sizeof(int)));
+  P.ginside = take((size_t)N);
   P.G = g->G; P.pitch = g->pitch; P.K = g->K; P.L = g->L; P.numSpokes = g->numSpokes; P.start = g->spokesStartIdx; P.N = N;
   P.unit = g->unit; P.mapX0 = g->mapX0; P.mapY0 = g->mapY0; P.maxRange = g->maxRange; P.wallHalf = g->wallHalf;
   P.sector = g->d_sector; P.radius = g->d_radius; P.axis = g->d_localAxis; P.ranges = d_ranges; P.pose = d_pose;
   P.grid = d_grid; P.prep = g_prep; P.slow = g_slow; P.status = d_status; P.slots = d_slots; P.reach = g_reach;
   update_prep_kernel<<<((N + 1) * 32 + 255) / 256, 256, 0, st>>>(P);      // + 1: the warp that computes the scan's reach
   SLAM_CUDA(cudaGetLastError());
+  update_group_kernel<<<1, UPD_GROUP_T, 0, st>>>(P);
+  SLAM_CUDA(cudaGetLastError());
   {
-    dim3 grid((g->L * g->L + 255) / 256, (N + UPD_CHUNK - 1) / UPD_CHUNK);
-    update_fast_kernel<<<grid, 256, 3 * g->numSpokes * sizeof(double), st>>>(P);
-    SLAM_CUDA(cudaGetLastError());
-  }
-  {
+    // grid.x: 256-cell tiles of the local patch (of its (L+2)^2 bounding box for the general path); grid.y: the
+    // blocks of a tile walk over the work items (<= N/32 + distinct shifts) with this stride -- small, because a tile
+    // that no beam can touch is discovered (and left) once per block
     const int side = g->L + 2;
-    dim3 grid((side * side + 255) / 256, 1);
-    update_general_kernel<<<grid, 256, 2 * g->L * sizeof(int), st>>>(P);
+    const int ny = std::max(1, std::min(N / (4 * UPD_ITEM), 8));
+    dim3 grid((side * side + 255) / 256, ny);
+    const size_t smem = std::max(3 * (size_t)g->K * sizeof(double), 2 * (size_t)g->L * sizeof(int));
+    update_apply_kernel<<<grid, 256, smem, st>>>(P);
     SLAM_CUDA(cudaGetLastError());
   }
   return 0;

@@ -193,6 +193,10 @@ class ParticleFilter:
         self._particles = None
         self.lastVariance = None
         self.lastResampleIdx = None
+        # hooks of the sharded filter: called at the start of a launch sequence / once the step's weights and poses are
+        # final (before the map update), so that the step's collective can overlap the map update on a side stream
+        self._preLaunch = None
+        self._afterFinish = None
 
     # ---- reference surface
     @property
@@ -304,6 +308,8 @@ class ParticleFilter:
         matched = self._matched[lo:hi]
         status = self.status[lo:hi]
         count, reading = rec["count"], rec["reading"]
+        if self._preLaunch is not None:
+            self._preLaunch()
         if count == 1:
             # matchedReading, confidence = reading, 1 (:123-125)
             matched.copy_(torch.tensor([reading['x'], reading['y'], reading['theta']], dtype=torch.float64))
@@ -346,6 +352,8 @@ class ParticleFilter:
                     self._traj.append(torch.zeros((N, 2), dtype=torch.float64, device=dev))
                 self._traj[-1][lo:hi] = matched[:, :2]
             self._trajCount = count
+        if self._afterFinish is not None and n == N:
+            self._afterFinish()
         with self.timer.section("update_kernels", dev):
             update_grids(self.geom, self.grids, n, d_stage[:K], matched, status, slots=self.slots[lo:hi])    # :133
         self.kernelLaunches += 3 + (0 if count == 1 else 3 + (1 if rec["mode"] == 1 else 0))
