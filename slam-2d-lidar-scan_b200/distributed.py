@@ -9,14 +9,12 @@ FastSlam.py:30-62).  Only when a resample fires do lattices move between ranks (
 Every rank seeds numpy identically and draws the uniforms of ALL N particles, using its own slice, so the result
 is bit-identical to the single-GPU run of the same N particles (partitioning is invisible).
 """
-import os
-
 import numpy as np
 import torch
 import torch.distributed as dist
 
 from . import _native as nat
-from .engine import StepResult, raise_for_status, copy_lattices, _stream
+from .engine import StepResult, SideTrigger, raise_for_status, copy_lattices, _stream
 from .fastslam import ParticleFilter
 
 
@@ -68,32 +66,11 @@ class ShardedParticleFilter:
         self.lastVariance = None
         self.lastResampleIdx = None
         # The step's collective + replicated normalisation depend on the matched poses / weights only, not on the map
-        # update that follows them: they run on a side stream next to the update kernels (the single-thread sequential
-        # normalisation over all N_total weights and the all-gather latency leave the critical path).
-        self.overlap = not os.environ.get("SLAM_NO_OVERLAP")
-        self._side = torch.cuda.Stream(device=dev)
-        self._evReady = torch.cuda.Event()
-        self._evDone = torch.cuda.Event()
-        self._pending = False
-        self.local._preLaunch = self._join
-        self.local._afterFinish = self._start_gather
-
-    def _join(self):
-        """The stream of the caller waits for the side-stream gather of the previous launch (if one is in flight)."""
-        if self._pending:
-            torch.cuda.current_stream(self.local.geom.device).wait_event(self._evDone)
-            self._pending = False
-
-    def _start_gather(self):
-        if not self.overlap:
-            return
-        dev = self.local.geom.device
-        self._evReady.record(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(self._side):
-            self._side.wait_event(self._evReady)
-            self._gather_body()
-            self._evDone.record(self._side)
-        self._pending = True
+        # update that follows them: they run on the local filter's side stream next to the update kernels (the
+        # single-thread sequential normalisation over all N_total weights and the all-gather latency leave the critical
+        # path), see engine.SideTrigger.
+        self.local._side = SideTrigger(dev, self._res)
+        self.local._sideBody = self._gather_body
 
     def updateParticles(self, reading, count):
         u = np.random.random_sample(self.numParticles) if count > 1 else None     # the global stream, all ranks
@@ -103,10 +80,11 @@ class ShardedParticleFilter:
         """The step's single collective + the replicated sequential normalisation.  No host synchronisation.  When the
         last launch already started them on the side stream (overlapped with the map update) this only joins; status
         bits raised by that map update itself (SLAM_ST_SCAN_OUTSIDE_MAP) are sticky and travel with the next gather."""
-        if self._pending:
-            self._join()
-            return
-        self._gather_body()
+        if self.local._side.pending:
+            self.local._side.join()
+        else:
+            self._gather_body()
+        self.local.weights.copy_(self._w[self.lo:self.hi])
 
     def _gather_body(self):
         pf = self.local
@@ -126,11 +104,14 @@ class ShardedParticleFilter:
                                                      _stream(dev)))
         self._res.reduce_status(self._stRanks, dev)
         pf.kernelLaunches += 3
-        pf.weights.copy_(self._w[self.lo:self.hi])
 
     def weightUnbalanced(self):
-        self.gather_and_normalize()
-        var, fired, bits = self._res.fetch()
+        if self.local._side.pending:
+            var, fired, bits = self.local._side.fetch()
+        else:
+            self._gather_body()
+            var, fired, bits = self._res.fetch()
+        self.local.weights.copy_(self._w[self.lo:self.hi])       # Particle.weight is raw until here
         self.local.d2hBytes += 24
         if self.local.ignoreMissingHeading:
             bits &= ~nat.ST_HEADING_MISSING

@@ -4,6 +4,7 @@ Host code only prepares constants with the reference's own Python/numpy expressi
 to what the reference would compute) and moves small buffers; all per-particle arithmetic runs in the sm_100a
 kernels of csrc/ through the C ABI (include/slam2d_b200.h).
 """
+import contextlib
 import ctypes as C
 import math
 
@@ -19,6 +20,15 @@ def _stream(dev):
 
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
+
+
+_NULL = contextlib.nullcontext()
+
+
+def on_device(dev):
+    """Context that makes ``dev`` the current CUDA device; free when it already is (the per-step host path enters it
+    half a dozen times)."""
+    return _NULL if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
 
 
 def gaussian_taps(sigma, truncate=4.0):
@@ -96,6 +106,7 @@ class MatcherEngine:
         self.handle = h
         self.nOffC = 2 * self.stageInfo[0]["nHalf"] + 1
         self._workspace = None               # device scratch, sized for the largest batch seen so far
+        self._radialDist = None
         self.zeroRv = torch.zeros(self.nOffC * self.nOffC, dtype=torch.float64, device=geom.device)
 
     def workspace_for(self, n):
@@ -124,10 +135,12 @@ class MatcherEngine:
         return np.arange(-n, n + 1)
 
     def radial_prior(self, estMovingDist):
-        ax = self.offset_axis(0)
-        xv, yv = np.meshgrid(ax, ax)
-        ul = self.coarseStep
-        d = np.sqrt((xv * ul) ** 2 + (yv * ul) ** 2)
+        d = self._radialDist
+        if d is None:                          # the offsets' distances do not depend on the step: computed once
+            ax = self.offset_axis(0)
+            xv, yv = np.meshgrid(ax, ax)
+            ul = self.coarseStep
+            d = self._radialDist = np.sqrt((xv * ul) ** 2 + (yv * ul) ** 2)
         rv = - (1 / (2 * self.moveRSigma ** 2)) * (d - estMovingDist) ** 2                # :101
         rv[np.abs(d - estMovingDist) > self.maxMoveDeviation] = -100                      # :102-103
         return rv
@@ -169,7 +182,7 @@ class MatcherEngine:
         ``grids`` (all lattices of the filter) instead of lattice p."""
         dev = self.geom.device
         ws = self.workspace_for(n)
-        with torch.cuda.device(dev):
+        with on_device(dev):
             nat.check(nat.lib.slam_match_scan_slots(
                 self.handle, grids.data_ptr(), _ptr(slots), grids.shape[0] if slots is not None else n, n,
                 d_ranges.data_ptr(), d_estPose.data_ptr(), d_rv.data_ptr(), _ptr(d_tw),
@@ -183,7 +196,7 @@ class MatcherEngine:
 
 def update_grids(geom, grids, n, d_ranges, d_pose, d_status, slots=None):
     ws = geom.update_workspace(n)
-    with torch.cuda.device(geom.device):
+    with on_device(geom.device):
         nat.check(nat.lib.slam_update_grid_slots(geom.c, grids.data_ptr(), _ptr(slots), n, d_ranges.data_ptr(),
                                                  d_pose.data_ptr(), d_status.data_ptr(), ws.data_ptr(), ws.numel(),
                                                  _stream(geom.device)))
@@ -237,11 +250,53 @@ class StepResult:
         self.bits = self.raw.view(torch.int32)[4:5]      # low word of out[2]
 
     def reduce_status(self, status, dev):
-        with torch.cuda.device(dev):
+        with on_device(dev):
             nat.check(nat.lib.slam_status_reduce(status.numel(), status.data_ptr(), self.bits.data_ptr(), _stream(dev)))
 
     def fetch(self):
         """-> (variance, fired, statusBits); synchronises."""
         h = self.raw[:24].cpu()
-        v = h[:16].view(torch.float64)
-        return float(v[0].item()), bool(v[1].item() != 0.0), int(h[16:20].view(torch.int32).item())
+        return self.parse(h)
+
+    @staticmethod
+    def parse(h):
+        a = h.numpy()
+        v = a[:16].view(np.float64)
+        return float(v[0]), bool(v[1] != 0.0), int(a[16:20].view(np.int32)[0])
+
+
+class SideTrigger:
+    """The end-of-step work that depends on the matched poses / weights only -- (all-gather,) sequential normalisation,
+    variance trigger, status reduction, the 24-byte read-back -- enqueued on a side stream as soon as those are final,
+    i.e. next to the map update instead of behind it.  ``weightUnbalanced`` then waits for the side stream alone: the
+    host returns (and prepares the next scan) while the map update is still running."""
+
+    def __init__(self, dev, res):
+        self.dev, self.res = dev, res
+        self.stream = torch.cuda.Stream(device=dev)
+        self.ready = torch.cuda.Event()
+        self.done = torch.cuda.Event()
+        self.host = torch.zeros(32, dtype=torch.uint8).pin_memory()
+        self.pending = False
+
+    def start(self, body):
+        """Run ``body()`` + the read-back on the side stream, ordered after everything enqueued so far."""
+        self.ready.record(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.ready)
+            body()
+            self.host.copy_(self.res.raw, non_blocking=True)
+            self.done.record(self.stream)
+        self.pending = True
+
+    def join(self):
+        """Stream-side join: work enqueued from now on sees the side stream's results.  No host synchronisation."""
+        if self.pending:
+            torch.cuda.current_stream(self.dev).wait_event(self.done)
+            self.pending = False
+
+    def fetch(self):
+        """-> (variance, fired, statusBits) of the pending side-stream work; the host waits for that work only."""
+        self.done.synchronize()
+        self.join()
+        return StepResult.parse(self.host)

@@ -10,12 +10,13 @@ RNG contract: the reference draws from numpy's global legacy RandomState -- one 
 here on the host, so a run seeded with ``np.random.seed`` consumes the identical stream.
 """
 import math
+import os
 
 import numpy as np
 import torch
 
 from . import _native as nat
-from .engine import (MatcherEngine, StepResult, raise_for_status, update_grids, plan_copy_elided, copy_lattices,
+from .engine import (MatcherEngine, StepResult, SideTrigger, on_device, _NULL, raise_for_status, update_grids, plan_copy_elided, copy_lattices,
                      _stream)
 from .geometry import LidarGeometry
 from .grid import OccupancyGrid
@@ -31,7 +32,7 @@ class KernelTimer:
         self.events = {}
 
     def section(self, name, dev):
-        return _Section(self, name, dev)
+        return _Section(self, name, dev) if self.enabled else _NULL
 
     def mean_ms(self):
         torch.cuda.synchronize()
@@ -168,6 +169,7 @@ class ParticleFilter:
         self._rv = torch.zeros(n2, **f64)
         K = self.geom.numSamplesPerRev
         self._stage_h = torch.zeros(K + n + n2, dtype=torch.float64).pin_memory()   # ranges | uniforms | rv
+        self._stage_np = self._stage_h.numpy()
         self._stage_d = torch.zeros(K + n + n2, **f64)
         self._stage_ev = torch.cuda.Event()
         self._stage_busy = False
@@ -193,10 +195,14 @@ class ParticleFilter:
         self._particles = None
         self.lastVariance = None
         self.lastResampleIdx = None
-        # hooks of the sharded filter: called at the start of a launch sequence / once the step's weights and poses are
-        # final (before the map update), so that the step's collective can overlap the map update on a side stream
-        self._preLaunch = None
-        self._afterFinish = None
+        # Once a step's weights and poses are final (before the map update) the normalisation + trigger start on a side
+        # stream (engine.SideTrigger); the sharded filter replaces the body by its all-gather + replicated normalisation.
+        # Status bits raised by the map update itself (SLAM_ST_SCAN_OUTSIDE_MAP) are sticky: they surface one
+        # weightUnbalanced() later.  SLAM_NO_OVERLAP=1 keeps everything on the caller's stream.
+        self.overlap = not os.environ.get("SLAM_NO_OVERLAP")
+        self._side = SideTrigger(dev, self._res)
+        self._sideBody = self._trigger_body
+        self._wn = torch.ones(n, **f64)      # side-stream copy: Particle.weight stays raw until weightUnbalanced()
 
     # ---- reference surface
     @property
@@ -214,14 +220,30 @@ class ParticleFilter:
                 self._update(i, i + 1, reading, count)
 
     def normalizeWeights(self):
-        self._normalize()
+        if self._side.pending:      # already normalised on the side stream, into the copy
+            self._side.join()
+            self.weights.copy_(self._wn)
+            return
+        self._normalize(self.weights)
+
+    def _trigger_body(self):
+        """Side stream: normalise a COPY of the weights (the raw Particle.weight stays readable until
+        weightUnbalanced() / normalizeWeights() is actually called), variance trigger, status reduction."""
+        self._wn.copy_(self.weights)
+        self._normalize(self._wn)
+        self._res.reduce_status(self.status, self.geom.device)
+        self.kernelLaunches += 1
 
     def weightUnbalanced(self):
         """Normalise, then the reference's variance trigger (FastSlam.py:30-41).  Synchronises (returns a bool)."""
-        self._normalize()
-        self._res.reduce_status(self.status, self.geom.device)
-        self.kernelLaunches += 1
-        var, fired, bits = self._res.fetch()
+        if self._side.pending:
+            var, fired, bits = self._side.fetch()
+            self.weights.copy_(self._wn)
+        else:
+            self._normalize(self.weights)
+            self._res.reduce_status(self.status, self.geom.device)
+            self.kernelLaunches += 1
+            var, fired, bits = self._res.fetch()
         self.d2hBytes += 24
         if self.ignoreMissingHeading:
             bits &= ~nat.ST_HEADING_MISSING
@@ -265,9 +287,9 @@ class ParticleFilter:
         self.grids.copy_(grid.unsqueeze(0).expand_as(self.grids))
 
     # ---- device step
-    def _normalize(self):
-        with torch.cuda.device(self.geom.device), self.timer.section("normalize_kernel", self.geom.device):
-            nat.check(nat.lib.slam_normalize_weights(self.numParticles, self.weights.data_ptr(), self._out.data_ptr(),
+    def _normalize(self, w):
+        with on_device(self.geom.device), self.timer.section("normalize_kernel", self.geom.device):
+            nat.check(nat.lib.slam_normalize_weights(self.numParticles, w.data_ptr(), self._out.data_ptr(),
                                                      _stream(self.geom.device)))
         self.kernelLaunches += 1
 
@@ -275,8 +297,8 @@ class ParticleFilter:
         """Host part of Particle.update: the raw-odometry scalars (identical for every particle), the RNG draws
         and the radial prior.  Fills a pinned staging row [ranges | uniforms | rv] and returns the launch record."""
         K, N, n2 = self.geom.numSamplesPerRev, self.numParticles, self.engine.nOffC ** 2
-        h = self._stage_h if out is None else out
-        h[:K] = torch.from_numpy(np.asarray(reading['range'], dtype=np.float64))
+        h = self._stage_np if out is None else out.numpy()      # numpy view of the (pinned) staging row
+        h[:K] = reading['range']
         rec = dict(count=count, reading=reading, mode=0, rawTurn=0.0, newRawHeading=None)
         if count == 1:
             return rec
@@ -291,13 +313,13 @@ class ParticleFilter:
         rec["rawTheta"], rec["prevRawTheta"] = raw['theta'], prevRaw['theta']
         if uniforms is None:
             uniforms = np.random.random_sample(n)                           # one draw per matchScan, particle order
-        h[K:K + n] = torch.from_numpy(np.ascontiguousarray(uniforms, dtype=np.float64))
-        h[K + N:K + N + n2] = torch.from_numpy(self.engine.radial_prior(estMovingDist).reshape(-1))
+        h[K:K + n] = uniforms
+        h[K + N:K + N + n2] = self.engine.radial_prior(estMovingDist).reshape(-1)
         return rec
 
     def _launch(self, lo, hi, rec, d_stage):
         """Device part of Particle.update for particles [lo, hi): kernel launches only, no host synchronisation."""
-        with torch.cuda.device(self.geom.device):
+        with on_device(self.geom.device):
             self._launch_on_device(lo, hi, rec, d_stage)
 
     def _launch_on_device(self, lo, hi, rec, d_stage):
@@ -305,45 +327,47 @@ class ParticleFilter:
         st = _stream(dev)
         eng = self.engine
         n2 = eng.nOffC ** 2
-        matched = self._matched[lo:hi]
-        status = self.status[lo:hi]
+        cut = (lambda t: t) if n == N else (lambda t: t[lo:hi])      # the whole batch: no views to build
+        matched = cut(self._matched)
+        status = cut(self.status)
+        prevMatched, prevHeading, hasHeading = cut(self.prevMatched), cut(self.prevHeading), cut(self.hasHeading)
+        est, phi, hasPhi, conf, weights = cut(self._est), cut(self._phi), cut(self._hasPhi), cut(self._conf), cut(self.weights)
         count, reading = rec["count"], rec["reading"]
-        if self._preLaunch is not None:
-            self._preLaunch()
+        self._side.join()          # a trigger nobody fetched: later launches still see its normalised weights
         if count == 1:
             # matchedReading, confidence = reading, 1 (:123-125)
             matched.copy_(torch.tensor([reading['x'], reading['y'], reading['theta']], dtype=torch.float64))
-            self.hasHeading[lo:hi] = 0
-            self.prevMatched[lo:hi] = matched
+            hasHeading.zero_()
+            prevMatched.copy_(matched)
         else:
             d_u = d_stage[K:K + n]
             d_rv = d_stage[K + N:K + N + n2]
             with self.timer.section("propose_kernel", dev):
                 nat.check(nat.lib.slam_propose_poses(
-                    n, self.prevMatched[lo:hi].data_ptr(), rec["rawTheta"], rec["prevRawTheta"], rec["mode"],
-                    rec["rawTurn"], self.prevHeading[lo:hi].data_ptr(), self.hasHeading[lo:hi].data_ptr(),
-                    self._est[lo:hi].data_ptr(), self._phi[lo:hi].data_ptr(), self._hasPhi[lo:hi].data_ptr(),
+                    n, prevMatched.data_ptr(), rec["rawTheta"], rec["prevRawTheta"], rec["mode"],
+                    rec["rawTurn"], prevHeading.data_ptr(), hasHeading.data_ptr(),
+                    est.data_ptr(), phi.data_ptr(), hasPhi.data_ptr(),
                     status.data_ptr(), st))
             tw = None
             if rec["mode"] == 1:
-                tw = self._tw[lo:hi]
+                tw = cut(self._tw)
                 with self.timer.section("priors_kernel", dev):
                     nat.check(nat.lib.slam_motion_priors(n, eng.stageInfo[0]["nHalf"], eng.heading_coef,
-                                                         self._phi[lo:hi].data_ptr(), self._hasPhi[lo:hi].data_ptr(),
+                                                         phi.data_ptr(), hasPhi.data_ptr(),
                                                          tw.data_ptr(), st))
             if self.matchEvents is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record(torch.cuda.current_stream(dev))
             with self.timer.section("match_kernel", dev):
-                eng.match(self.grids, n, d_stage[:K], self._est[lo:hi], d_rv, tw, d_u, matched,
-                          self._conf[lo:hi], self._idx[lo:hi], status, slots=self.slots[lo:hi])
+                eng.match(self.grids, n, d_stage[:K], est, d_rv, tw, d_u, matched,
+                          conf, cut(self._idx), status, slots=cut(self.slots))
             if self.matchEvents is not None:
                 ev1.record(torch.cuda.current_stream(dev))
                 self.matchEvents.append((ev0, ev1))
             with self.timer.section("finish_kernel", dev):
-                nat.check(nat.lib.slam_finish_step(n, matched.data_ptr(), self._conf[lo:hi].data_ptr(),
-                                                   self.prevMatched[lo:hi].data_ptr(), self.prevHeading[lo:hi].data_ptr(),
-                                                   self.hasHeading[lo:hi].data_ptr(), self.weights[lo:hi].data_ptr(), st))
+                nat.check(nat.lib.slam_finish_step(n, matched.data_ptr(), conf.data_ptr(),
+                                                   prevMatched.data_ptr(), prevHeading.data_ptr(),
+                                                   hasHeading.data_ptr(), weights.data_ptr(), st))
         if self.keepTrajectory:
             if n == N:
                 self._traj.append(matched[:, :2].clone())
@@ -352,10 +376,10 @@ class ParticleFilter:
                     self._traj.append(torch.zeros((N, 2), dtype=torch.float64, device=dev))
                 self._traj[-1][lo:hi] = matched[:, :2]
             self._trajCount = count
-        if self._afterFinish is not None and n == N:
-            self._afterFinish()
+        if self.overlap and n == N:
+            self._side.start(self._sideBody)
         with self.timer.section("update_kernels", dev):
-            update_grids(self.geom, self.grids, n, d_stage[:K], matched, status, slots=self.slots[lo:hi])    # :133
+            update_grids(self.geom, self.grids, n, d_stage[:K], matched, status, slots=cut(self.slots))    # :133
         self.kernelLaunches += 3 + (0 if count == 1 else 3 + (1 if rec["mode"] == 1 else 0))
 
     def _grow(self):
