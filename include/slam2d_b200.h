@@ -215,6 +215,12 @@ int slam_finish_step(int32_t N, const double* d_matched, const double* d_conf, d
  * d_out[0] = variance, d_out[1] = 1.0 if the trigger fires else 0.0. */
 int slam_normalize_weights(int32_t N, double* d_weights, double* d_out, void* stream);
 
+/* The whole end-of-step trigger in one launch (FastSlam.py:30-48 + the status check): d_weightsOut[i] =
+ * d_weightsIn[i] / sum (sequential float64 order; the two may alias), d_out[0] = variance, d_out[1] = trigger, and the
+ * low 32 bits of d_out[2] = bitwise OR of the nStatus status words (untouched when nStatus == 0). */
+int slam_step_trigger(int32_t N, const double* d_weightsIn, double* d_weightsOut, const int32_t* d_status,
+                      int32_t nStatus, double* d_out, void* stream);
+
 /* d_out[0] = bitwise OR of the N per-particle status words.  Status words are sticky: every kernel ORs its bits
  * in, nothing clears them but the caller (numpy would have raised at the first one: ScanMatcher_OGBased.py:125-138). */
 int slam_status_reduce(int32_t N, const int32_t* d_status, int32_t* d_out, void* stream);

@@ -70,6 +70,7 @@ SYMBOLS = {
     "slam_propose_poses": (C.c_int, [_I, _V, _D, _D, _I, _D, _V, _V, _V, _V, _V, _V, _V]),
     "slam_finish_step": (C.c_int, [_I, _V, _V, _V, _V, _V, _V, _V]),
     "slam_normalize_weights": (C.c_int, [_I, _V, _V, _V]),
+    "slam_step_trigger": (C.c_int, [_I, _V, _V, _V, _I, _V, _V]),
     "slam_status_reduce": (C.c_int, [_I, _V, _V, _V]),
     "slam_resample_indices": (C.c_int, [_I, _V, _V, _V, _V, _V]),
     "slam_gather_particles": (C.c_int, [C.POINTER(Geometry), _I, _V, _V, _V, _V, _V, _I, _V, _V]),

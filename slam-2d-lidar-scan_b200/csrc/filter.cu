@@ -47,13 +47,25 @@ __global__ void finish_kernel(int N, const double* matched, const double* conf, 
 // contract (one thread adds, in index order); the independent per-element work (loads, divisions, squares) is done
 // by the whole block through a shared-memory tile so the adding thread never waits on memory or on a divide.
 constexpr int NORM_T = 1024;
-__global__ void __launch_bounds__(NORM_T) normalize_kernel(int N, double* w, double* out) {
+// `src` may differ from `w` (out-of-place: the raw weights stay readable); with `status` the kernel also ORs the nStatus
+// status words into the low word of out[2] -- the whole end-of-step trigger in one launch.
+__global__ void __launch_bounds__(NORM_T) normalize_kernel(int N, const double* src, double* w, double* out,
+                                                           const int* status, int nStatus) {
   __shared__ double tile[NORM_T];
   __shared__ double s_sum;
+  __shared__ int s_or;
   const int tid = threadIdx.x;
+  if (status) {
+    if (tid == 0) s_or = 0;
+    __syncthreads();
+    int v = 0;
+    for (int i = tid; i < nStatus; i += NORM_T) v |= status[i];
+    v = __reduce_or_sync(0xffffffffu, v);
+    if ((tid & 31) == 0 && v) atomicOr(&s_or, v);
+  }
   double s = 0.0;
   for (int i0 = 0; i0 < N; i0 += NORM_T) {
-    if (i0 + tid < N) tile[tid] = w[i0 + tid];
+    if (i0 + tid < N) tile[tid] = src[i0 + tid];
     __syncthreads();
     if (tid == 0) {
       const int n = min(NORM_T, N - i0);
@@ -69,7 +81,7 @@ __global__ void __launch_bounds__(NORM_T) normalize_kernel(int N, double* w, dou
   double var = 0.0;
   for (int i0 = 0; i0 < N; i0 += NORM_T) {
     if (i0 + tid < N) {
-      const double wi = ddiv(w[i0 + tid], s);
+      const double wi = ddiv(src[i0 + tid], s);
       w[i0 + tid] = wi;
       const double d = dsub(wi, invN);
       tile[tid] = dmul(d, d);
@@ -87,6 +99,7 @@ __global__ void __launch_bounds__(NORM_T) normalize_kernel(int N, double* w, dou
     const double thr = dadd(dmul(a, a), dmul(dsub(n, 1.000000000000001), dmul(invN, invN)));
     out[0] = var;
     out[1] = var > thr ? 1.0 : 0.0;
+    if (status) reinterpret_cast<int*>(out + 2)[0] = s_or;      // published by the barriers of the loops above
   }
 }
 
@@ -181,7 +194,17 @@ extern "C" int slam_finish_step(int32_t N, const double* d_matched, const double
 
 extern "C" int slam_normalize_weights(int32_t N, double* d_weights, double* d_out, void* stream) {
   if (N <= 0 || !d_weights || !d_out) return fail(SLAM_E_BADARG, "slam_normalize_weights: bad argument");
-  normalize_kernel<<<1, NORM_T, 0, (cudaStream_t)stream>>>(N, d_weights, d_out);
+  normalize_kernel<<<1, NORM_T, 0, (cudaStream_t)stream>>>(N, d_weights, d_weights, d_out, nullptr, 0);
+  SLAM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int slam_step_trigger(int32_t N, const double* d_weightsIn, double* d_weightsOut, const int32_t* d_status,
+                                 int32_t nStatus, double* d_out, void* stream) {
+  if (N <= 0 || !d_weightsIn || !d_weightsOut || !d_out || (nStatus > 0 && !d_status))
+    return fail(SLAM_E_BADARG, "slam_step_trigger: bad argument");
+  normalize_kernel<<<1, NORM_T, 0, (cudaStream_t)stream>>>(N, d_weightsIn, d_weightsOut, d_out,
+                                                           nStatus > 0 ? d_status : nullptr, nStatus);
   SLAM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -69,8 +69,11 @@ class ShardedParticleFilter:
         # update that follows them: they run on the local filter's side stream next to the update kernels (the
         # single-thread sequential normalisation over all N_total weights and the all-gather latency leave the critical
         # path), see engine.SideTrigger.
-        self.local._side = SideTrigger(dev, self._res)
-        self.local._sideBody = self._gather_body
+        if self.world > 1:
+            self.local._side = SideTrigger(dev, self._res)
+            self.local._sideBody = self._gather_body
+        else:                                 # one rank: nothing to gather -- the local filter's own trigger
+            self._res, self._w = self.local._res, self.local._wn
 
     def updateParticles(self, reading, count):
         u = np.random.random_sample(self.numParticles) if count > 1 else None     # the global stream, all ranks
@@ -83,7 +86,7 @@ class ShardedParticleFilter:
         if self.local._side.pending:
             self.local._side.join()
         else:
-            self._gather_body()
+            self.local._sideBody()
         self.local.weights.copy_(self._w[self.lo:self.hi])
 
     def _gather_body(self):
@@ -99,17 +102,14 @@ class ShardedParticleFilter:
             self._all[0].copy_(self._mine)
         self._w.copy_(self._all[:, :nL, 0].reshape(-1))
         self._stRanks.copy_(self._all[:, nL, 0])
-        with torch.cuda.device(dev):
-            nat.check(nat.lib.slam_normalize_weights(self.numParticles, self._w.data_ptr(), self._out.data_ptr(),
-                                                     _stream(dev)))
-        self._res.reduce_status(self._stRanks, dev)
-        pf.kernelLaunches += 3
+        self._res.trigger(self._w, self._w, self._stRanks, dev)      # normalise in place + trigger + OR of the ranks' bits
+        pf.kernelLaunches += 2
 
     def weightUnbalanced(self):
         if self.local._side.pending:
             var, fired, bits = self.local._side.fetch()
         else:
-            self._gather_body()
+            self.local._sideBody()
             var, fired, bits = self._res.fetch()
         self.local.weights.copy_(self._w[self.lo:self.hi])       # Particle.weight is raw until here
         self.local.d2hBytes += 24
@@ -121,6 +121,8 @@ class ShardedParticleFilter:
 
     def poses(self):
         """[N][3] poses of all particles as of the last gather (host numpy)."""
+        if self.world == 1:
+            return self.local.poses()
         return self._all[:, :self.hi - self.lo, 1:].reshape(-1, 3).cpu().numpy()
 
     def resample(self):

@@ -176,7 +176,7 @@ class MatcherEngine:
         return dbg, bufs
 
     def match(self, grids, n, d_ranges, d_estPose, d_rv, d_tw, d_uniforms, d_outPose, d_outConf, d_outIdx, d_status,
-              debug=None, slots=None):
+              debug=None, slots=None, stream=None):
         """slam_match_scan on the geometry's device, current stream.  All arguments are device tensors (or None).
         Status bits are OR-ed into d_status (sticky).  ``slots`` (int32 [n]): particle p reads lattice slots[p] of
         ``grids`` (all lattices of the filter) instead of lattice p."""
@@ -187,19 +187,20 @@ class MatcherEngine:
                 self.handle, grids.data_ptr(), _ptr(slots), grids.shape[0] if slots is not None else n, n,
                 d_ranges.data_ptr(), d_estPose.data_ptr(), d_rv.data_ptr(), _ptr(d_tw),
                 _ptr(d_uniforms), d_outPose.data_ptr(), d_outConf.data_ptr(), d_outIdx.data_ptr(), d_status.data_ptr(),
-                ws.data_ptr(), ws.numel(), C.byref(debug) if debug is not None else None, _stream(dev)))
+                ws.data_ptr(), ws.numel(), C.byref(debug) if debug is not None else None,
+                _stream(dev) if stream is None else stream))
 
     def volume_shape(self, stage):
         n = 2 * self.stageInfo[stage]["nHalf"] + 1
         return (len(self.stageInfo[stage]["thetas"]), n, n)
 
 
-def update_grids(geom, grids, n, d_ranges, d_pose, d_status, slots=None):
-    ws = geom.update_workspace(n)
+def update_grids(geom, grids, n, d_ranges, d_pose, d_status, slots=None, stream=None):
+    st = _stream(geom.device) if stream is None else stream
+    ws = geom.update_workspace(n, st)
     with on_device(geom.device):
         nat.check(nat.lib.slam_update_grid_slots(geom.c, grids.data_ptr(), _ptr(slots), n, d_ranges.data_ptr(),
-                                                 d_pose.data_ptr(), d_status.data_ptr(), ws.data_ptr(), ws.numel(),
-                                                 _stream(geom.device)))
+                                                 d_pose.data_ptr(), d_status.data_ptr(), ws.data_ptr(), ws.numel(), st))
 
 
 def plan_copy_elided(idx, slots):
@@ -252,6 +253,12 @@ class StepResult:
     def reduce_status(self, status, dev):
         with on_device(dev):
             nat.check(nat.lib.slam_status_reduce(status.numel(), status.data_ptr(), self.bits.data_ptr(), _stream(dev)))
+
+    def trigger(self, wIn, wOut, status, dev):
+        """normalise (wIn -> wOut, sequential float64), variance + trigger -> out[0:2], OR of ``status`` -> bits: one launch."""
+        with on_device(dev):
+            nat.check(nat.lib.slam_step_trigger(wIn.numel(), wIn.data_ptr(), wOut.data_ptr(), status.data_ptr(),
+                                                status.numel(), self.out.data_ptr(), _stream(dev)))
 
     def fetch(self):
         """-> (variance, fired, statusBits); synchronises."""

@@ -227,11 +227,11 @@ class ParticleFilter:
         self._normalize(self.weights)
 
     def _trigger_body(self):
-        """Side stream: normalise a COPY of the weights (the raw Particle.weight stays readable until
-        weightUnbalanced() / normalizeWeights() is actually called), variance trigger, status reduction."""
-        self._wn.copy_(self.weights)
-        self._normalize(self._wn)
-        self._res.reduce_status(self.status, self.geom.device)
+        """One launch (slam_step_trigger), normally on the side stream: normalise the weights into a COPY (the raw
+        Particle.weight stays readable until weightUnbalanced() / normalizeWeights() is actually called), variance
+        trigger, OR of the status words."""
+        with self.timer.section("normalize_kernel", self.geom.device):
+            self._res.trigger(self.weights, self._wn, self.status, self.geom.device)
         self.kernelLaunches += 1
 
     def weightUnbalanced(self):
@@ -240,10 +240,9 @@ class ParticleFilter:
             var, fired, bits = self._side.fetch()
             self.weights.copy_(self._wn)
         else:
-            self._normalize(self.weights)
-            self._res.reduce_status(self.status, self.geom.device)
-            self.kernelLaunches += 1
+            self._trigger_body()
             var, fired, bits = self._res.fetch()
+            self.weights.copy_(self._wn)
         self.d2hBytes += 24
         if self.ignoreMissingHeading:
             bits &= ~nat.ST_HEADING_MISSING
@@ -360,7 +359,7 @@ class ParticleFilter:
                 ev0.record(torch.cuda.current_stream(dev))
             with self.timer.section("match_kernel", dev):
                 eng.match(self.grids, n, d_stage[:K], est, d_rv, tw, d_u, matched,
-                          conf, cut(self._idx), status, slots=cut(self.slots))
+                          conf, cut(self._idx), status, slots=cut(self.slots), stream=st)
             if self.matchEvents is not None:
                 ev1.record(torch.cuda.current_stream(dev))
                 self.matchEvents.append((ev0, ev1))
@@ -379,7 +378,7 @@ class ParticleFilter:
         if self.overlap and n == N:
             self._side.start(self._sideBody)
         with self.timer.section("update_kernels", dev):
-            update_grids(self.geom, self.grids, n, d_stage[:K], matched, status, slots=cut(self.slots))    # :133
+            update_grids(self.geom, self.grids, n, d_stage[:K], matched, status, slots=cut(self.slots), stream=st)    # :133
         self.kernelLaunches += 3 + (0 if count == 1 else 3 + (1 if rec["mode"] == 1 else 0))
 
     def _grow(self):

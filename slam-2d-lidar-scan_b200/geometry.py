@@ -49,7 +49,7 @@ class LidarGeometry:
         self.spokesStartIdx = int(((self.numSpokes / 2 - numSamplesPerRev) / 2) % self.numSpokes)   # :30
         self._build_sector_tables()
         self.device = require_cuda(device)
-        self._updWs = {}
+        self._updWs, self._updWsN = {}, {}
         dev = self.device
         self.d_gridX = torch.from_numpy(self.gridX).to(dev)
         self.d_gridY = torch.from_numpy(self.gridY).to(dev)
@@ -107,11 +107,14 @@ class LidarGeometry:
     def contains(self, x0, x1, y0, y1):
         return x0 >= self.mapXLim[0] and x1 <= self.mapXLim[1] and y0 >= self.mapYLim[0] and y1 <= self.mapYLim[1]
 
-    def update_workspace(self, n):
+    def update_workspace(self, n, stream=None):
         """Device scratch of slam_update_grid for n particles, one buffer per CUDA stream (grown on demand)."""
-        key = torch.cuda.current_stream(self.device).cuda_stream
-        need = nat.lib.slam_update_workspace_bytes(n)
+        key = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
         ws = self._updWs.get(key)
+        if ws is not None and self._updWsN.get(key, 0) >= n:
+            return ws
+        need = nat.lib.slam_update_workspace_bytes(n)
+        self._updWsN[key] = n
         if ws is None or ws.numel() < need:
             ws = torch.empty(need, dtype=torch.uint8, device=self.device)
             self._updWs[key] = ws
