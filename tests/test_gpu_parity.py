@@ -161,6 +161,16 @@ def test_weights_trigger_and_resample_known_answers(S):
         nat.check(nat.lib.slam_normalize_weights(n, w.data_ptr(), out.data_ptr(), st))
         assert np.array_equal(w.cpu().numpy(), g["wn_%d" % n])
         assert bool(out[1].item()) == bool(g["fired_%d" % n][0])
+        # the fused end-of-step trigger: same normalisation out of place (raw weights untouched) + OR of the status words
+        raw = torch.from_numpy(g["w0_%d" % n].copy()).to(dev)
+        wn = torch.zeros(n, dtype=torch.float64, device=dev)
+        res = torch.zeros(4, dtype=torch.float64, device=dev)
+        status = torch.zeros(n, dtype=torch.int32, device=dev)
+        status[n // 2], status[n - 1] = 8, 16
+        nat.check(nat.lib.slam_step_trigger(n, raw.data_ptr(), wn.data_ptr(), status.data_ptr(), n, res.data_ptr(), st))
+        assert np.array_equal(wn.cpu().numpy(), g["wn_%d" % n]) and np.array_equal(raw.cpu().numpy(), g["w0_%d" % n])
+        assert res[0].item() == out[0].item() and res[1].item() == out[1].item()
+        assert int(res.view(torch.int32)[4].item()) == 24
         u = torch.from_numpy(g["u_%d" % n].copy()).to(dev)
         cdf = torch.zeros(n, dtype=torch.float64, device=dev)
         idx = torch.zeros(n, dtype=torch.int32, device=dev)

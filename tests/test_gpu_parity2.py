@@ -285,6 +285,47 @@ def _oracle_stage(ref, mp, x, y, th, rng, ul, sigma, miss, searchRadius, estDist
 
 
 @pytest.mark.gpu
+def test_grouped_map_update_many_headings_and_a_patch_leaving_the_map(S):
+    """slam_update_grid groups the particles by sector shift: 70 particles with 40 distinct headings (several work items,
+    partial groups), one pose half a cell off the lattice (general path in the same launch) and one patch that leaves
+    the lattice (cells outside are skipped, SLAM_ST_SCAN_OUTSIDE_MAP is raised for that particle only); counts
+    identical to the oracle's per-particle OccupancyGrid.updateOccupancyGrid (OccupancyGrid.py:127-152)."""
+    from slam_2d_lidar_scan_b200.engine import update_grids
+    nat = S._native
+    init = {"x": 0.0, "y": 0.0}
+    args = (30, 30, init, 0.1, np.pi, 180, 10, 0.5)
+    og = S.OccupancyGrid(*args)
+    geom = og.geom
+    rng = np.random.default_rng(7)
+    n = 70
+    ranges = np.round(rng.uniform(1.0, 12.0, 180), 2)
+    poses = np.zeros((n, 3))
+    poses[:, 0] = np.round(rng.uniform(-3, 3, n), 1)            # on the lattice: pure shifts
+    poses[:, 1] = np.round(rng.uniform(-3, 3, n), 1)
+    poses[:, 2] = (np.arange(n) % 40) * (2 * np.pi / 360) * 1.7 - 0.6
+    poses[5, 0] += 0.05                                         # half a cell off: rint ties -> general path
+    poses[9, :2] = (9.0, -2.0)                                  # patch reaches x = 19 > 15: leaves the lattice
+    dev = geom.device
+    grids = geom.new_grids(n)
+    status = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_r = torch.from_numpy(ranges).to(dev)
+    d_p = torch.from_numpy(poses).to(dev)
+    for _ in range(2):
+        update_grids(geom, grids, n, d_r, d_p, status)
+    torch.cuda.synchronize()
+    st = status.cpu().numpy()
+    assert st[9] == nat.ST_SCAN_OUTSIDE_MAP and not st[np.arange(n) != 9].any()
+    G = geom.G
+    host = grids.cpu().numpy()[:, :, :G, :]
+    for i in (0, 3, 5, 17, 39, 40, 41, 69):
+        ref = O.OccupancyGrid(*args)
+        rd = {"x": poses[i, 0], "y": poses[i, 1], "theta": poses[i, 2], "range": list(ranges)}
+        ref.updateOccupancyGrid(rd)
+        ref.updateOccupancyGrid(rd)
+        assert np.array_equal(host[i, :, :, 0], ref.occupancyGridVisited), i       # both [row = y][col = x]
+        assert np.array_equal(host[i, :, :, 1], ref.occupancyGridTotal), i
+
+
 def test_stage_methods_match_the_oracle_stage_by_stage(S, frames):
     """The reference's public stage API (ScanMatcher_OGBased.py:20-45, 81-176): frameSearchSpace ->
     searchToMatch (coarse, argmax and sampled, with and without heading prior) -> frameSearchSpace -> searchToMatch

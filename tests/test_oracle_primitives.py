@@ -60,3 +60,29 @@ def test_linspace():
     for th in (-0.463373, 1.25, 31.29101329218997):
         a = P.linspace(th - np.pi / 2, th + np.pi / 2, 180)
         assert np.array_equal(a, np.linspace(th - np.pi / 2, th + np.pi / 2, num=180))
+
+
+def test_division_by_a_fixed_cell_size_with_a_hoisted_reciprocal_is_ieee_division():
+    """csrc/match.cu `ddiv_rcp`: the index division (q - begin) / unitLength (ScanMatcher_OGBased.py:174-175) uses the
+    correctly rounded reciprocal r = RN(1 / b) once per list: q = RN(a r), rem = a - b q (exact in one FMA),
+    RN(q + rem r).  Markstein's theorem says this IS the correctly rounded quotient; checked here in exact rational
+    arithmetic (fractions -> float conversion rounds to nearest even) against Python's IEEE division."""
+    from fractions import Fraction
+    rng = np.random.default_rng(11)
+
+    def fma(x, y, z):
+        return float(Fraction(x) * Fraction(y) + Fraction(z))
+
+    divisors = [0.02, 0.05, 0.1, 0.25, 0.5, 0.05 * 5, 0.02 * 5, 0.1 * 2] + list(rng.uniform(0.01, 1.0, 8))
+    for b in divisors:
+        r = 1.0 / b
+        cells = rng.integers(0, 1300, 700)
+        samples = np.concatenate([rng.uniform(0.0, 70.0, 700),
+                                  cells * b,                                   # exact multiples of the cell size
+                                  cells * b + rng.choice([-1, 1], 700) * np.spacing(cells * b)])
+        for a in samples:
+            a = float(a)
+            q = a * r
+            rem = fma(-b, q, a)
+            got = fma(rem, r, q)
+            assert got == a / b, (a, b, got, a / b)
