@@ -9,7 +9,9 @@ holds the workload's particle count (c3: 1024 particles, 1001x1001 lattices @0.0
 
   value   whole-job particle-scans/s with the step's inputs already resident in HBM (pre-staged), CUDA-event timed
   e2e     the same through the public API (ParticleFilter.updateParticles + weightUnbalanced) with HOST readings:
-          per step one pinned H2D copy (ranges | uniforms | radial prior) and a D2H read of (variance, trigger, status)
+          per step one pinned H2D copy (ranges | uniforms | radial prior) and a D2H read of (variance, trigger, status).
+          In both arms the normalisation / trigger (/ all-gather) of a step run on a side stream next to its map update
+          (engine.SideTrigger); the timed regions end with a full device synchronisation
   roofline  fused match kernel: N * B_match algorithmic bytes / its mean CUDA-event duration, vs the measured HBM peak;
           `traffic` comes from profiles/r2_match_traffic.json only while that file's hash of csrc/match.cu + common.cuh
           still matches the sources (tools/ncu_traffic.py stamps it), else null

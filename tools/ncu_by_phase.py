@@ -63,6 +63,8 @@ elif len(sys.argv) > 3:      # full source text as captured in the report (lines
 bounds = []
 for text, name in MARKS:
     hit = [ln for ln, s in src.items() if text.strip("\n") in s and (not text.endswith("\n") or s.rstrip() == text.rstrip("\n"))]
+    if text.endswith("\n") and bounds:      # a bare `} else {`: the first one AFTER the previous marker (the scatter's range path)
+        hit = [ln for ln in hit if ln > bounds[-1][0]]
     if hit:
         bounds.append((min(hit), name))
 bounds.sort()
