@@ -182,9 +182,12 @@ int slam_motion_priors(int32_t N, int32_t nHalf, double coef, const double* d_ph
 /* (visited, total) := (1, 2) for N lattices (OccupancyGrid.py:13-14). */
 int slam_grid_init(const slam_geometry* geom, float* d_grid, int32_t N, void* stream);
 
-/* OccupancyGrid.updateOccupancyGrid for N particles (OccupancyGrid.py:127-152).  Map-cell-owned: every map
- * cell is written by exactly one thread, reproducing numpy's once-per-statement fancy `+=` even when two
- * lidar-local cells round to the same map cell.  d_pose [N][3]; d_status |= SLAM_ST_SCAN_OUTSIDE_MAP. */
+/* OccupancyGrid.updateOccupancyGrid for N particles (OccupancyGrid.py:127-152).  Owner computes: every map cell of a
+ * lattice is updated by exactly one thread (float reductions at the L2 -- the counts are small integers, so the adds are
+ * exact and order-independent), reproducing numpy's once-per-statement fancy `+=` even when two lidar-local cells round
+ * to the same map cell (poses half a cell off the lattice take a map-cell-owned path inside the same launch).  Particles
+ * are grouped by their sector shift first, so the empty / hit classification of a local cell is evaluated once per
+ * group.  numSpokes <= 8192.  d_pose [N][3]; d_status |= SLAM_ST_SCAN_OUTSIDE_MAP (cells outside the lattice are skipped). */
 int slam_update_grid(const slam_geometry* geom, float* d_grid, int32_t N, const double* d_ranges,
                      const double* d_pose, int32_t* d_status, void* d_workspace, size_t workspaceBytes, void* stream);
 /* Device scratch slam_update_grid needs for N particles (per call; may be shared by calls on one stream). */
