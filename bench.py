@@ -251,10 +251,12 @@ def run_b200(args):
     # weights (the lattices keep integrating the scans): the reference never resamples a power-of-two population
     # (SURVEY A9), so hundreds of consecutive sampled steps would only measure a diverging random walk.
     def snapshot():
+        spf.flush()                      # a deferred copy-back of normalised weights lands before they are saved
         return (pf.prevMatched.clone(), pf.prevHeading.clone(), pf.hasHeading.clone(), pf.weights.clone(),
                 list(pf._prevRaw), list(pf._prevRawHeading))
 
     def restore(sn):
+        spf.flush()
         pf.prevMatched.copy_(sn[0]); pf.prevHeading.copy_(sn[1]); pf.hasHeading.copy_(sn[2]); pf.weights.copy_(sn[3])
         pf._prevRaw, pf._prevRawHeading = list(sn[4]), list(sn[5])
 
@@ -285,6 +287,7 @@ def run_b200(args):
             for i in range(W, W + K):
                 pf._launch(0, nLocal, recs[i], rows[i])
                 spf.gather_and_normalize()
+        spf.flush()                      # the last step's side-stream work is inside the timed region
         e1.record(torch.cuda.current_stream(dev))
         sync_all()
     pf._prevRaw, pf._prevRawHeading = [prevRaw] * nLocal, [prevHead] * nLocal

@@ -80,14 +80,18 @@ class ShardedParticleFilter:
         self.local._update(0, self.hi - self.lo, reading, count, uniforms=None if u is None else u[self.lo:self.hi])
 
     def gather_and_normalize(self):
-        """The step's single collective + the replicated sequential normalisation.  No host synchronisation.  When the
-        last launch already started them on the side stream (overlapped with the map update) this only joins; status
-        bits raised by that map update itself (SLAM_ST_SCAN_OUTSIDE_MAP) are sticky and travel with the next gather."""
-        if self.local._side.pending:
-            self.local._side.join()
-        else:
+        """The step's single collective + the replicated sequential normalisation, without host synchronisation and
+        without waiting on the device either: when the last launch started them on the side stream this only notes that
+        the normalised weights must be copied back before the next step's weight update (ParticleFilter._settle), so the
+        collective overlaps the map update AND the next step's match kernel.  flush() completes it on the caller's stream.
+        Status bits raised by the map update itself (SLAM_ST_SCAN_OUTSIDE_MAP) are sticky and travel with the next gather."""
+        if not self.local._side.pending:
             self.local._sideBody()
-        self.local.weights.copy_(self._w[self.lo:self.hi])
+        self.local._copyBack = self._w[self.lo:self.hi]
+
+    def flush(self):
+        """Stream-side completion of a gather_and_normalize(): Particle.weight holds the normalised weights afterwards."""
+        self.local._settle()
 
     def _gather_body(self):
         pf = self.local
@@ -111,6 +115,7 @@ class ShardedParticleFilter:
         else:
             self.local._sideBody()
             var, fired, bits = self._res.fetch()
+        self.local._copyBack = None
         self.local.weights.copy_(self._w[self.lo:self.hi])       # Particle.weight is raw until here
         self.local.d2hBytes += 24
         if self.local.ignoreMissingHeading:

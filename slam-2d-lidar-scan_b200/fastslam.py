@@ -203,6 +203,7 @@ class ParticleFilter:
         self._side = SideTrigger(dev, self._res)
         self._sideBody = self._trigger_body
         self._wn = torch.ones(n, **f64)      # side-stream copy: Particle.weight stays raw until weightUnbalanced()
+        self._copyBack = None                # normalised weights whose copy into .weights is deferred (see _settle)
 
     # ---- reference surface
     @property
@@ -220,6 +221,7 @@ class ParticleFilter:
                 self._update(i, i + 1, reading, count)
 
     def normalizeWeights(self):
+        self._copyBack = None
         if self._side.pending:      # already normalised on the side stream, into the copy
             self._side.join()
             self.weights.copy_(self._wn)
@@ -236,6 +238,7 @@ class ParticleFilter:
 
     def weightUnbalanced(self):
         """Normalise, then the reference's variance trigger (FastSlam.py:30-41).  Synchronises (returns a bool)."""
+        self._copyBack = None
         if self._side.pending:
             var, fired, bits = self._side.fetch()
             self.weights.copy_(self._wn)
@@ -332,8 +335,8 @@ class ParticleFilter:
         prevMatched, prevHeading, hasHeading = cut(self.prevMatched), cut(self.prevHeading), cut(self.hasHeading)
         est, phi, hasPhi, conf, weights = cut(self._est), cut(self._phi), cut(self._hasPhi), cut(self._conf), cut(self.weights)
         count, reading = rec["count"], rec["reading"]
-        self._side.join()          # a trigger nobody fetched: later launches still see its normalised weights
         if count == 1:
+            self._settle()
             # matchedReading, confidence = reading, 1 (:123-125)
             matched.copy_(torch.tensor([reading['x'], reading['y'], reading['theta']], dtype=torch.float64))
             hasHeading.zero_()
@@ -363,6 +366,7 @@ class ParticleFilter:
             if self.matchEvents is not None:
                 ev1.record(torch.cuda.current_stream(dev))
                 self.matchEvents.append((ev0, ev1))
+            self._settle()         # the proposal and the match above did not need the previous step's trigger
             with self.timer.section("finish_kernel", dev):
                 nat.check(nat.lib.slam_finish_step(n, matched.data_ptr(), conf.data_ptr(),
                                                    prevMatched.data_ptr(), prevHeading.data_ptr(),
@@ -380,6 +384,16 @@ class ParticleFilter:
         with self.timer.section("update_kernels", dev):
             update_grids(self.geom, self.grids, n, d_stage[:K], matched, status, slots=cut(self.slots), stream=st)    # :133
         self.kernelLaunches += 3 + (0 if count == 1 else 3 + (1 if rec["mode"] == 1 else 0))
+
+    def _settle(self):
+        """Called before a launch sequence overwrites weights / poses.  The previous step's side-stream trigger must
+        have read them (stream-side join, no host synchronisation), and a deferred copy-back of its normalised weights
+        lands now.  Until here the next step's proposal and match ran next to that trigger: with several ranks the
+        all-gather (and the skew between ranks) overlaps a whole match kernel."""
+        self._side.join()
+        if self._copyBack is not None:
+            self.weights.copy_(self._copyBack)
+            self._copyBack = None
 
     def _grow(self):
         """All lattices double around the map centre (geometry.grown): the filter's maps become the lattices a filter
